@@ -1,0 +1,228 @@
+/*
+ * jtb_check.h — C ABI of the B200-native history checker (libjtb_check.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of nurturenature/jepsen-tigerbeetle that this
+ * repo accelerates: the history checkers that sit behind the Clojure protocol
+ * `jepsen.checker/Checker` (`(check [this test history opts]) -> {:valid? ...}`), composed by the
+ * reference at
+ *     src/tigerbeetle/workloads/set_full.clj:155-158   (independent/checker ∘ compose{set-full, read-all-invoked-adds})
+ *     src/tigerbeetle/tests/ledger.clj:363-367         (compose{:SI checker, ...})
+ *     src/tigerbeetle/core.clj:139-146                 (top-level compose)
+ *
+ * A JVM host (JNI) or any FFI binds exactly these entry points; all arguments are plain pointers and
+ * sizes owned by the caller for the duration of the call.  Nothing here is a torch type.
+ *
+ * Verdict coding follows jepsen.checker/merge-valid (false dominates :unknown dominates true):
+ *     JTB_VALID (0) < JTB_UNKNOWN (1) < JTB_INVALID (2)   so that merging == max.
+ */
+#ifndef JTB_CHECK_H
+#define JTB_CHECK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JTB_ABI_VERSION 1
+
+/* ---- verdict lattice (jepsen.checker/merge-valid) ------------------------------------------- */
+#define JTB_VALID   0
+#define JTB_UNKNOWN 1
+#define JTB_INVALID 2
+
+/* ---- op :type (knossos.op/{invoke?,ok?,fail?,info?}) ----------------------------------------- */
+#define JTB_T_INVOKE 0
+#define JTB_T_OK     1
+#define JTB_T_FAIL   2
+#define JTB_T_INFO   3
+
+/* ---- op :f opcodes ----------------------------------------------------------------------------
+ * register / cas-register (knossos.model):  READ a=value|JTB_NIL ; WRITE a=value ; CAS a=old b=new
+ * set (knossos.model/set, jepsen.checker/set-full; set_full.clj:29-31,128-134):
+ *                                           ADD a=element ; READ payload=element ids
+ * bank (tests/ledger.clj:89-114 after ledger->bank):
+ *                                           TRANSFER a=amount b=debit-acct c=credit-acct ;
+ *                                           READ payload=(account id, balance) pairs
+ */
+#define JTB_F_READ     0
+#define JTB_F_WRITE    1
+#define JTB_F_CAS      2
+#define JTB_F_ADD      3
+#define JTB_F_TRANSFER 4
+
+#define JTB_NIL INT32_MIN /* Clojure nil in an int32 field (a nil register read matches any state) */
+
+/* ---- op flags --------------------------------------------------------------------------------- */
+#define JTB_FLAG_FINAL 1u /* :final? true  (set_full.clj:45, tests/ledger.clj:78,84) */
+
+/* ---- models for the linearizability search ---------------------------------------------------- */
+#define JTB_MODEL_REGISTER     0 /* knossos.model/register      */
+#define JTB_MODEL_CAS_REGISTER 1 /* knossos.model/cas-register  */
+#define JTB_MODEL_SET          2 /* knossos.model/set (grow-only) */
+#define JTB_MODEL_BANK         3 /* bank-transfer model implied by tests/ledger.clj:89-152 */
+
+#define JTB_MAX_ACCOUNTS 8 /* core.clj:208-210 default (vec (range 1 9)) */
+
+/*
+ * Flattened history, struct-of-arrays, little-endian, events in history (:index) order.
+ * Independent keys (jepsen.independent tuples, set_full.clj:31,44,116,134) are a CSR partition:
+ * shard s owns events [shard_off[s], shard_off[s+1]); inside a shard events keep history order.
+ * A history without independent keys has n_shards = 1, shard_off = {0, n_events}.
+ * Events of non-client processes (:nemesis) carry process < 0 and are ignored by every checker
+ * (tests/ledger.clj:94,204,228,262).
+ */
+typedef struct jtb_history {
+    int64_t n_events;
+    const uint8_t*  type;        /* [n_events] JTB_T_*                                              */
+    const uint8_t*  f;           /* [n_events] JTB_F_*                                              */
+    const uint8_t*  flags;       /* [n_events] JTB_FLAG_* (may be NULL = all zero)                  */
+    const int32_t*  process;     /* [n_events] :process, <0 = not a client                          */
+    const int32_t*  index;       /* [n_events] original :index (reported back as witness)           */
+    const int64_t*  time_ns;     /* [n_events] :time                                                */
+    const int32_t*  a;           /* [n_events] see opcodes                                          */
+    const int32_t*  b;           /* [n_events]                                                      */
+    const int32_t*  c;           /* [n_events]                                                      */
+    const int64_t*  payload_off; /* [n_events] offset into payload (in int32 units)                 */
+    const int32_t*  payload_len; /* [n_events] number of int32 in this event's payload, -1 = nil    */
+    const int32_t*  payload;     /* [n_payload]                                                     */
+    int64_t n_payload;
+    int32_t n_shards;
+    const int64_t*  shard_off;   /* [n_shards+1]                                                    */
+    const int64_t*  key_ids;     /* [n_shards] the independent key of each shard (may be NULL)      */
+} jtb_history;
+
+typedef struct jtb_model {
+    int32_t kind;                         /* JTB_MODEL_*                                            */
+    int32_t init_value;                   /* register / cas-register initial value (JTB_NIL = nil)  */
+    int32_t n_accounts;                   /* bank: (count (:accounts test)) <= JTB_MAX_ACCOUNTS     */
+    int32_t account_ids[JTB_MAX_ACCOUNTS];/* bank: (:accounts test), core.clj:208-210               */
+    int32_t init_balance[JTB_MAX_ACCOUNTS];/* bank: starting balances (db.clj:118-127 => zeros)     */
+    int32_t negative_balances_ok;         /* bank: (:negative-balances? test), core.clj:217-219     */
+} jtb_model;
+
+/* Options for a context.  Zero-initialise, then set what you need. */
+typedef struct jtb_opts {
+    int32_t  device;            /* CUDA device ordinal for this context                              */
+    int32_t  reserved0;
+    uint64_t table_bytes;       /* visited-config table size in HBM (0 = default 4 GiB)              */
+    uint64_t max_configs;       /* search budget: stop with JTB_UNKNOWN after this many (0 = table)   */
+    uint32_t time_budget_ms;    /* 0 = unlimited                                                      */
+    uint32_t search_ctas;       /* 0 = one persistent CTA per SM × resident CTAs                      */
+} jtb_opts;
+
+/* Per-shard output of the linearizability search (knossos analysis map). */
+typedef struct jtb_lin_shard {
+    int32_t  valid;             /* JTB_VALID / JTB_UNKNOWN / JTB_INVALID                              */
+    int32_t  witness_index;     /* :index of the :ok completion that cannot be linearized (:op), -1   */
+    int32_t  previous_ok_index; /* :index of the last :ok completion before it (:previous-ok), -1     */
+    int32_t  cause;             /* JTB_CAUSE_* when valid == JTB_UNKNOWN                              */
+    uint64_t configs_explored;  /* distinct (linearized-set, model-state) configs inserted            */
+    uint64_t probes;            /* visited-table probes (hits + misses)                               */
+} jtb_lin_shard;
+
+#define JTB_CAUSE_NONE          0
+#define JTB_CAUSE_TABLE_FULL    1 /* visited table exhausted (knossos: out of memory -> :unknown)    */
+#define JTB_CAUSE_BUDGET        2 /* max_configs / time budget reached                                */
+#define JTB_CAUSE_TOO_WIDE      3 /* > 64 concurrently open completed ops, or key does not fit        */
+
+typedef struct jtb_lin_result {
+    int32_t  valid;             /* merge-valid over shards                                            */
+    int32_t  n_failures;        /* number of shards whose verdict is not JTB_VALID (:failures)        */
+    uint64_t configs_explored;  /* sum over shards                                                    */
+    uint64_t probes;            /* sum over shards                                                    */
+    uint64_t hbm_bytes_algorithmic; /* key_bytes*(probes + inserts), SURVEY §8(d)                     */
+    uint32_t key_bytes;         /* bytes per visited-table slot used by this call (16/32/64)          */
+    uint32_t reserved0;
+    double   seconds_kernel;    /* device time of the search kernels (CUDA events)                    */
+    double   seconds_total;     /* host wall time of the call incl. flatten-prep, H2D, D2H            */
+} jtb_lin_result;
+
+/* Per-shard output of jepsen.checker/set-full. Element lists are returned through
+ * caller-provided buffers in jtb_setfull_out. */
+typedef struct jtb_setfull_shard {
+    int32_t valid;
+    int32_t attempt_count, stable_count, lost_count, never_read_count, stale_count, duplicated_count;
+    int32_t reserved0;
+    int64_t stable_latency_max_ms; /* max stable-latency (0 if none)  */
+    int64_t lost_latency_max_ms;   /* max lost-latency (0 if none)    */
+} jtb_setfull_shard;
+
+/* Per-element classification codes written to jtb_setfull_out.elem_outcome */
+#define JTB_SF_NEVER_READ 0
+#define JTB_SF_STABLE     1
+#define JTB_SF_LOST       2
+
+typedef struct jtb_setfull_out {
+    jtb_setfull_shard* shards;     /* [n_shards] required                                             */
+    /* optional per-element detail, CSR by shard over tracked elements in first-add-invoke order:     */
+    int64_t  elem_capacity;        /* capacity of the arrays below (0 = not wanted)                   */
+    int64_t* elem_off;             /* [n_shards+1]                                                    */
+    int32_t* elem_id;              /* element value                                                   */
+    uint8_t* elem_outcome;         /* JTB_SF_*                                                        */
+    int64_t* elem_latency_ms;      /* stable-latency / lost-latency in ms (0 for never-read)          */
+    int32_t* elem_dup_count;       /* max multiplicity seen in one read if > 1, else 0                */
+    int32_t  valid;                /* merge-valid over shards                                          */
+    int32_t  n_failures;
+    double   seconds_kernel;
+    double   seconds_total;
+} jtb_setfull_out;
+
+/* bank SI checker (tests/ledger.clj:127-192) error classes, in `cond` precedence order */
+#define JTB_BANK_OK             0
+#define JTB_BANK_UNEXPECTED_KEY 1
+#define JTB_BANK_NIL_BALANCE    2
+#define JTB_BANK_WRONG_TOTAL    3
+#define JTB_BANK_NEGATIVE_VALUE 4
+
+typedef struct jtb_bank_result {
+    int32_t valid;
+    int32_t reserved0;
+    int64_t read_count;            /* :read-count  */
+    int64_t error_count;           /* :error-count */
+    int32_t first_error_index;     /* :index of (:op :first-error), -1                                 */
+    int32_t first_error_type;      /* JTB_BANK_*                                                        */
+    int64_t count_by_type[5];      /* (:count (errors type))                                            */
+    int32_t first_index_by_type[5];/* :index of :first                                                  */
+    int32_t last_index_by_type[5]; /* :index of :last                                                   */
+    int32_t worst_index_by_type[5];/* :index of :worst (err-badness, tests/ledger.clj:116-125)          */
+    int64_t lowest_total, highest_total;       /* :wrong-total :lowest / :highest totals                */
+    int32_t lowest_index, highest_index;
+    double  seconds_kernel;
+    double  seconds_total;
+} jtb_bank_result;
+
+typedef struct jtb_ctx jtb_ctx;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+int         jtb_abi_version(void);
+int         jtb_device_count(void);                 /* number of CUDA devices, <0 on error          */
+jtb_ctx*    jtb_create(const jtb_opts* opts);       /* NULL on failure (no CUDA device etc.)        */
+void        jtb_destroy(jtb_ctx* ctx);
+const char* jtb_last_error(const jtb_ctx* ctx);     /* valid until the next call on ctx             */
+
+/* ---- hot path A9: jepsen.checker/linearizable -> knossos analysis ---------------------------- *
+ * Replaces (checker/linearizable {:model m}) — no call site in the reference; it would be added to
+ * the compose maps at set_full.clj:156-158 / tests/ledger.clj:363-367.
+ * shards[n_shards] is caller-allocated.  Returns 0 on success (verdict in out), <0 on error
+ * (jtb_last_error; glue throws so that jepsen's check-safe yields {:valid? :unknown}).          */
+int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m,
+                           jtb_lin_shard* shards, jtb_lin_result* out);
+
+/* ---- hot path A4: (checker/set-full {:linearizable? L}) at set_full.clj:157 ------------------ */
+int jtb_check_set_full(jtb_ctx* ctx, const jtb_history* h, int linearizable, jtb_setfull_out* out);
+
+/* ---- hot path A8: bank SI checker, tests/ledger.clj:154-192 (after ledger->bank) -------------- */
+int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* accounts,
+                          int64_t total_amount, jtb_bank_result* out);
+
+/* ---- K2 in isolation: visited-table probe/insert microbenchmark (roofline evidence) ----------- *
+ * Inserts n_keys pseudo-random 128-bit keys then probes them `rounds` times; returns device
+ * seconds for insert and probe phases.  variant selects the probe path.          */
+int jtb_table_bench(jtb_ctx* ctx, uint64_t n_keys, int variant, int rounds,
+                    double* insert_seconds, double* probe_seconds, uint64_t* found);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JTB_CHECK_H */

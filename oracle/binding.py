@@ -1,0 +1,108 @@
+"""ctypes binding of the CPU oracle (libjtb_oracle.so).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from jepsen_tigerbeetle_b200 import abi
+from jepsen_tigerbeetle_b200.history import CModel, FlatHistory, as_c_history
+
+ALGO_BRUTE, ALGO_LINEAR, ALGO_WGL, ALGO_WGL_COMPACT = 0, 1, 2, 3
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libjtb_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("lin_oracle.cpp", "scan_oracle.cpp", "oracle_common.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "jtb_check.h"))
+    stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.jtbo_last_error.restype = C.c_char_p
+        _LIB.jtbo_scan_last_error.restype = C.c_char_p
+    return _LIB
+
+
+def check_linearizable(h: FlatHistory, model: CModel, algo: int = ALGO_WGL_COMPACT,
+                       max_configs: int = 0, canon_info: bool = True, n_threads: int = 1) -> dict:
+    ch = as_c_history(h)
+    shards = (abi.CLinShard * h.n_shards)()
+    res = abi.CLinResult()
+    rc = lib().jtbo_check_linearizable(C.byref(ch), C.byref(model), algo, C.c_uint64(max_configs),
+                                       int(canon_info), n_threads, shards, C.byref(res))
+    if rc != 0:
+        raise RuntimeError(lib().jtbo_last_error().decode())
+    return {
+        "valid": res.valid, "n_failures": res.n_failures, "configs": res.configs_explored,
+        "probes": res.probes, "seconds": res.seconds_total,
+        "shards": [{"valid": s.valid, "witness_index": s.witness_index,
+                    "previous_ok_index": s.previous_ok_index, "cause": s.cause,
+                    "configs": s.configs_explored, "probes": s.probes} for s in shards],
+    }
+
+
+def check_set_full(h: FlatHistory, linearizable: bool = True) -> dict:
+    ch = as_c_history(h)
+    shards = (abi.CSetFullShard * h.n_shards)()
+    cap = int(np.count_nonzero((h.f == 3) & (h.type == 0))) + 1
+    elem_off = np.zeros(h.n_shards + 1, np.int64)
+    elem_id = np.zeros(cap, np.int32)
+    elem_outcome = np.zeros(cap, np.uint8)
+    elem_lat = np.zeros(cap, np.int64)
+    elem_dup = np.zeros(cap, np.int32)
+    out = abi.CSetFullOut(C.cast(shards, C.c_void_p), cap, elem_off.ctypes.data, elem_id.ctypes.data,
+                          elem_outcome.ctypes.data, elem_lat.ctypes.data, elem_dup.ctypes.data)
+    rc = lib().jtbo_check_set_full(C.byref(ch), int(linearizable), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(lib().jtbo_scan_last_error().decode())
+    return abi_setfull_to_dict(out, shards, elem_off, elem_id, elem_outcome, elem_lat, elem_dup)
+
+
+def abi_setfull_to_dict(out, shards, elem_off, elem_id, elem_outcome, elem_lat, elem_dup) -> dict:
+    n = int(elem_off[-1])
+    fields = ("valid", "attempt_count", "stable_count", "lost_count", "never_read_count",
+              "stale_count", "duplicated_count", "stable_latency_max_ms", "lost_latency_max_ms")
+    return {
+        "valid": out.valid, "n_failures": out.n_failures, "seconds": out.seconds_total,
+        "seconds_kernel": out.seconds_kernel,
+        "shards": [{f: getattr(s, f) for f in fields} for s in shards],
+        "elem_off": elem_off.copy(), "elem_id": elem_id[:n].copy(),
+        "elem_outcome": elem_outcome[:n].copy(), "elem_latency_ms": elem_lat[:n].copy(),
+        "elem_dup_count": elem_dup[:n].copy(),
+    }
+
+
+def check_bank_totals(h: FlatHistory, model: CModel, total_amount: int = 0) -> dict:
+    ch = as_c_history(h)
+    res = abi.CBankResult()
+    rc = lib().jtbo_check_bank_totals(C.byref(ch), C.byref(model), C.c_int64(total_amount),
+                                      C.byref(res))
+    if rc != 0:
+        raise RuntimeError(lib().jtbo_scan_last_error().decode())
+    return bank_to_dict(res)
+
+
+def bank_to_dict(res) -> dict:
+    return {
+        "valid": res.valid, "read_count": res.read_count, "error_count": res.error_count,
+        "first_error_index": res.first_error_index, "first_error_type": res.first_error_type,
+        "count_by_type": list(res.count_by_type),
+        "first_index_by_type": list(res.first_index_by_type),
+        "last_index_by_type": list(res.last_index_by_type),
+        "worst_index_by_type": list(res.worst_index_by_type),
+        "lowest_total": res.lowest_total, "highest_total": res.highest_total,
+        "lowest_index": res.lowest_index, "highest_index": res.highest_index,
+        "seconds": res.seconds_total, "seconds_kernel": res.seconds_kernel,
+    }

@@ -1,0 +1,494 @@
+// lin_oracle.cpp — TEST INFRASTRUCTURE ONLY.  CPU restatement of the linearizability analyses behind
+// jepsen.checker/linearizable (see oracle_common.h for the parity statement).
+//
+// Four mutually independent deciders over the same preprocessed history:
+//   ALGO_BRUTE   (0)  permutation enumeration, no memoisation, n <= ~9 ops          (ground truth)
+//   ALGO_LINEAR  (1)  knossos.linear: event-ordered set of configs, just-in-time    
+//   ALGO_WGL     (2)  knossos.wgl: Wing–Gong/Lowe DFS over a doubly linked entry list with
+//                     lift/unlift and a cache of (linearized BitSet, model) — keyed literally on the
+//                     full N-bit set, as Knossos does                                
+//   ALGO_WGL_COMPACT (3) the same DFS, cache keyed on the exact window form
+//                     (first un-linearized return, mask of open ops, crashed bits, state).  This is
+//                     the TIMED CPU BASELINE (bench.py cpu_baseline / --impl reference): Knossos'
+//                     own cache would need N/8 bytes per config.
+// Witness (":op") is defined canonically as the earliest :ok completion c such that the history
+// prefix through c is not linearizable == the furthest return any branch was blocked at.
+#include <chrono>
+#include <functional>
+#include <thread>
+#include <atomic>
+#include <set>
+
+#include "oracle_common.h"
+
+using namespace jtbo;
+
+namespace {
+
+enum { ALGO_BRUTE = 0, ALGO_LINEAR = 1, ALGO_WGL = 2, ALGO_WGL_COMPACT = 3 };
+
+struct Verdict {
+    int valid = JTB_VALID;
+    int witness_ret = -1;  // index into sh.rets
+    int cause = JTB_CAUSE_NONE;
+    uint64_t configs = 0, probes = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// open-addressing set of fixed-width keys (W 64-bit words); all-zero = empty (keys set bit 63 of w0)
+class KeySet {
+  public:
+    explicit KeySet(int w) : W(w) { rehash(1 << 12); }
+    bool insert(const uint64_t* k) {  // true if new
+        if ((n + 1) * 10 > cap * 6) rehash(cap * 2);
+        size_t i = hash(k) & (cap - 1);
+        for (;;) {
+            uint64_t* s = &slots[i * W];
+            if (s[0] == 0) { std::memcpy(s, k, W * 8); ++n; return true; }
+            if (std::memcmp(s, k, W * 8) == 0) return false;
+            i = (i + 1) & (cap - 1);
+        }
+    }
+    size_t size() const { return n; }
+
+  private:
+    int W;
+    size_t cap = 0, n = 0;
+    std::vector<uint64_t> slots;
+    uint64_t hash(const uint64_t* k) const {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < W; ++i) {
+            h ^= k[i];
+            h *= 0xFF51AFD7ED558CCDull;
+            h ^= h >> 32;
+        }
+        return h;
+    }
+    void rehash(size_t ncap) {
+        std::vector<uint64_t> old;
+        old.swap(slots);
+        size_t ocap = cap;
+        cap = ncap;
+        slots.assign(cap * W, 0);
+        n = 0;
+        for (size_t i = 0; i < ocap; ++i)
+            if (old[i * W]) {
+                size_t j = hash(&old[i * W]) & (cap - 1);
+                while (slots[j * W]) j = (j + 1) & (cap - 1);
+                std::memcpy(&slots[j * W], &old[i * W], W * 8);
+                ++n;
+            }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// ALGO_BRUTE
+struct Brute {
+    const Shard& sh;
+    std::vector<int> ids;      // ops considered (invoked before the prefix end)
+    std::vector<char> must;    // must be linearized (returned within the prefix)
+    std::vector<int> perm;
+    std::vector<char> used;
+    bool found = false;
+    explicit Brute(const Shard& s) : sh(s) {}
+
+    bool order_ok() const {
+        for (size_t i = 0; i < perm.size(); ++i)
+            for (size_t j = i + 1; j < perm.size(); ++j) {
+                // perm[i] linearized before perm[j]: illegal if perm[j] returned before perm[i] was invoked
+                if (sh.ops[perm[j]].ret_pos < sh.ops[perm[i]].inv_pos) return false;
+            }
+        // every op left out must not be required; and a left-out op imposes nothing
+        return true;
+    }
+    void rec(State st, SetState ss, int n_must_left, int prefix_end) {
+        if (found) return;
+        if (n_must_left == 0 && order_ok()) {
+            // additionally: an included op must not be linearized after a *required* op that ... covered by order_ok
+            found = true;
+            return;
+        }
+        for (size_t k = 0; k < ids.size(); ++k) {
+            if (used[k]) continue;
+            const Op& o = sh.ops[ids[k]];
+            bool legal = true;  // real-time order: o may not follow an op invoked after o returned
+            for (int x : perm)
+                if (o.ret_pos < sh.ops[x].inv_pos) { legal = false; break; }
+            if (!legal) continue;
+            State st2 = st;
+            SetState ss2 = ss;
+            if (!step(sh, o, st2, &ss2)) continue;
+            used[k] = 1;
+            perm.push_back(ids[k]);
+            rec(st2, ss2, n_must_left - (must[k] ? 1 : 0), prefix_end);
+            perm.pop_back();
+            used[k] = 0;
+            if (found) return;
+        }
+    }
+    // is the prefix of the history up to and including position `end` linearizable?
+    bool prefix_ok(int end) {
+        ids.clear(); must.clear();
+        int n_must = 0;
+        for (int i = 0; i < (int)sh.ops.size(); ++i)
+            if (sh.ops[i].inv_pos <= end) {
+                ids.push_back(i);
+                bool m = sh.ops[i].ret_pos <= end;
+                must.push_back(m);
+                n_must += m;
+            }
+        used.assign(ids.size(), 0);
+        perm.clear();
+        found = false;
+        SetState ss;
+        ss.cnt.assign(sh.n_elems, 0);
+        rec(sh.init, ss, n_must, end);
+        return found;
+    }
+    Verdict run() {
+        Verdict v;
+        if (sh.ops.size() > 12) throw std::runtime_error("brute force oracle limited to 12 ops");
+        for (int j = 0; j < (int)sh.rets.size(); ++j)
+            if (!prefix_ok(sh.ops[sh.rets[j]].ret_pos)) {
+                v.valid = JTB_INVALID;
+                v.witness_ret = j;
+                return v;
+            }
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// ALGO_LINEAR (knossos.linear, just-in-time)
+struct Linear {
+    const Shard& sh;
+    uint64_t max_configs;
+    explicit Linear(const Shard& s, uint64_t mc) : sh(s), max_configs(mc) {}
+    struct Cfg {
+        std::vector<int> ahead;  // sorted op ids linearized but not yet returned (crashed: forever)
+        State st;
+        bool operator<(const Cfg& o) const {
+            if (ahead != o.ahead) return ahead < o.ahead;
+            if (st.reg != o.st.reg) return st.reg < o.st.reg;
+            return std::memcmp(st.bal, o.st.bal, sizeof st.bal) < 0;
+        }
+    };
+    std::vector<int> returned_cnt;  // set model: element multiplicity among returned adds
+
+    bool do_step(const Cfg& c, const Op& o, State& st2) const {
+        st2 = c.st;
+        if (sh.model->kind != JTB_MODEL_SET) return step(sh, o, st2, nullptr);
+        if (o.f == JTB_F_ADD) return true;
+        if (o.impossible) return false;
+        // state = returned adds ∪ ahead adds
+        std::set<int> extra;
+        for (int x : c.ahead)
+            if (sh.ops[x].f == JTB_F_ADD && returned_cnt[sh.ops[x].a] == 0) extra.insert(sh.ops[x].a);
+        int distinct = 0;
+        for (int e = 0; e < sh.n_elems; ++e) distinct += returned_cnt[e] > 0;
+        distinct += (int)extra.size();
+        if ((int)o.elems.size() != distinct) return false;
+        for (int e : o.elems)
+            if (returned_cnt[e] == 0 && !extra.count(e)) return false;
+        return true;
+    }
+
+    Verdict run() {
+        Verdict v;
+        returned_cnt.assign(sh.n_elems, 0);
+        // events
+        std::vector<std::pair<int, int>> evs;  // (pos, op or ~op for return)
+        for (int i = 0; i < (int)sh.ops.size(); ++i) {
+            evs.push_back({sh.ops[i].inv_pos, i});
+            if (!sh.ops[i].crashed) evs.push_back({sh.ops[i].ret_pos, ~i});
+        }
+        std::sort(evs.begin(), evs.end());
+        std::set<Cfg> configs;
+        configs.insert(Cfg{{}, sh.init});
+        std::vector<int> pending;
+        int ret_no = 0;
+        for (auto& ev : evs) {
+            if (ev.second >= 0) { pending.push_back(ev.second); continue; }
+            int o = ~ev.second;
+            std::set<Cfg> out, seen;
+            for (const Cfg& c0 : configs) {
+                std::vector<Cfg> stack{c0};
+                while (!stack.empty()) {
+                    Cfg c = stack.back();
+                    stack.pop_back();
+                    if (!seen.insert(c).second) continue;
+                    v.configs++;
+                    if (max_configs && v.configs > max_configs) {
+                        v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_BUDGET; return v;
+                    }
+                    auto it = std::lower_bound(c.ahead.begin(), c.ahead.end(), o);
+                    if (it != c.ahead.end() && *it == o) {
+                        Cfg r = c;
+                        r.ahead.erase(r.ahead.begin() + (it - c.ahead.begin()));
+                        out.insert(r);
+                        continue;
+                    }
+                    for (int x : pending) {
+                        if (std::binary_search(c.ahead.begin(), c.ahead.end(), x)) continue;
+                        State st2;
+                        if (!do_step(c, sh.ops[x], st2)) continue;
+                        Cfg n;
+                        n.st = st2;
+                        if (x == o) {
+                            n.ahead = c.ahead;
+                            out.insert(n);
+                        } else {
+                            n.ahead = c.ahead;
+                            n.ahead.insert(std::lower_bound(n.ahead.begin(), n.ahead.end(), x), x);
+                            stack.push_back(n);
+                        }
+                    }
+                }
+            }
+            if (out.empty()) {
+                v.valid = JTB_INVALID;
+                v.witness_ret = ret_no;
+                return v;
+            }
+            // o has returned: it leaves `pending`; for the set model its element is now permanent
+            pending.erase(std::find(pending.begin(), pending.end(), o));
+            if (sh.model->kind == JTB_MODEL_SET && sh.ops[o].f == JTB_F_ADD) returned_cnt[sh.ops[o].a]++;
+            configs.swap(out);
+            ++ret_no;
+        }
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// ALGO_WGL / ALGO_WGL_COMPACT  (knossos.wgl)
+struct WGL {
+    const Shard& sh;
+    bool compact, canon;
+    uint64_t max_configs;
+    WGL(const Shard& s, bool compact_, bool canon_, uint64_t mc)
+        : sh(s), compact(compact_), canon(canon_), max_configs(mc) {}
+
+    Verdict run() {
+        Verdict v;
+        const int n = (int)sh.ops.size();
+        const int n_ret = (int)sh.rets.size();
+        if (n_ret == 0) return v;
+        if (compact && sh.n_slots > 64) { v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_TOO_WIDE; return v; }
+        // entry list: node 2i = call of op i, 2i+1 = return of op i; node 2n = head sentinel
+        const int HEAD = 2 * n;
+        std::vector<int> nxt(2 * n + 1, -1), prv(2 * n + 1, -1);
+        {
+            std::vector<std::pair<int, int>> ent;
+            for (int i = 0; i < n; ++i) {
+                ent.push_back({sh.ops[i].inv_pos, 2 * i});
+                if (!sh.ops[i].crashed) ent.push_back({sh.ops[i].ret_pos, 2 * i + 1});
+            }
+            std::sort(ent.begin(), ent.end());
+            int last = HEAD;
+            for (auto& e : ent) { nxt[last] = e.second; prv[e.second] = last; last = e.second; }
+            nxt[last] = -1;
+        }
+        auto unlink = [&](int x) {
+            nxt[prv[x]] = nxt[x];
+            if (nxt[x] >= 0) prv[nxt[x]] = prv[x];
+        };
+        auto relink = [&](int x) {
+            nxt[prv[x]] = x;
+            if (nxt[x] >= 0) prv[nxt[x]] = x;
+        };
+        // crashed op numbering for the compact key
+        std::vector<int> crash_no(n, -1);
+        int n_crashed = 0;
+        for (int i = 0; i < n; ++i)
+            if (sh.ops[i].crashed) crash_no[i] = n_crashed++;
+        const bool reg_model = sh.model->kind <= JTB_MODEL_CAS_REGISTER;
+        const bool bank_model = sh.model->kind == JTB_MODEL_BANK;
+        int W;
+        if (compact) W = 2 + (n_crashed + 63) / 64;
+        else W = 1 + (n + 63) / 64 + (bank_model ? 4 : 0);
+        KeySet cache(W);
+        std::vector<uint64_t> key(W);
+        std::vector<uint64_t> lin((n + 63) / 64, 0), crashbits((n_crashed + 63) / 64 + 1, 0);
+        std::vector<int> cls_count(sh.n_classes, 0);
+        std::vector<int> ret_rank(n, -1);
+        for (int j = 0; j < n_ret; ++j) ret_rank[sh.rets[j]] = j;
+
+        struct Frame { int op; State st; int rj; uint64_t mask; };
+        std::vector<Frame> stack;
+        State st = sh.init;
+        SetState ss;
+        ss.cnt.assign(sh.n_elems, 0);
+        int rj = 0;          // first un-linearized return
+        uint64_t mask = 0;   // slots of linearized completed ops that return after rets[rj]
+        int max_rj = 0;
+        int n_lin_completed = 0;
+
+        auto make_key = [&](int rj2, uint64_t mask2, const State& st2) {
+            if (compact) {
+                key[0] = (1ull << 63) | ((uint64_t)(uint32_t)rj2 << 32) |
+                         (reg_model ? (uint64_t)(uint32_t)st2.reg : 0ull);
+                key[1] = mask2;
+                for (int i = 0; i < W - 2; ++i) key[2 + i] = crashbits[i];
+            } else {
+                key[0] = (1ull << 63) | (reg_model ? (uint64_t)(uint32_t)st2.reg : 0ull);
+                int nw = (n + 63) / 64;
+                for (int i = 0; i < nw; ++i) key[1 + i] = lin[i];
+                if (bank_model) std::memcpy(&key[1 + nw], st2.bal, 32);
+            }
+        };
+
+        int entry = nxt[HEAD];
+        while (true) {
+            if (n_lin_completed == n_ret) break;  // every :ok op linearized -> valid
+            if (entry >= 0 && !(entry & 1)) {
+                // ---- call entry: try to linearize it
+                const int i = entry >> 1;
+                const Op& o = sh.ops[i];
+                bool eligible = true;
+                if (canon && o.crashed && cls_count[o.cls] != o.rank_in_cls) eligible = false;
+                State st2 = st;
+                bool ok = eligible && step(sh, o, st2, &ss);
+                if (ok) {
+                    // tentative new config
+                    int rj2 = rj;
+                    uint64_t mask2 = mask;
+                    lin[i >> 6] |= 1ull << (i & 63);
+                    if (o.crashed) crashbits[crash_no[i] >> 6] |= 1ull << (crash_no[i] & 63);
+                    else if (sh.rets[rj] == i) {
+                        ++rj2;
+                        while (rj2 < n_ret && (lin[sh.rets[rj2] >> 6] >> (sh.rets[rj2] & 63) & 1)) {
+                            mask2 &= ~(1ull << sh.ops[sh.rets[rj2]].slot);
+                            ++rj2;
+                        }
+                    } else mask2 |= 1ull << o.slot;
+                    make_key(rj2, mask2, st2);
+                    v.probes++;
+                    if (cache.insert(key.data())) {
+                        v.configs++;
+                        stack.push_back(Frame{i, st, rj, mask});
+                        st = st2; rj = rj2; mask = mask2;
+                        if (rj > max_rj) max_rj = rj;
+                        if (!o.crashed) { n_lin_completed++; unlink(2 * i + 1); }
+                        else cls_count[o.cls]++;
+                        unlink(2 * i);
+                        entry = nxt[HEAD];
+                        if (max_configs && v.configs >= max_configs && n_lin_completed != n_ret) {
+                            v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_BUDGET; return v;
+                        }
+                        continue;
+                    }
+                    // already seen: undo tentative marks
+                    lin[i >> 6] &= ~(1ull << (i & 63));
+                    if (o.crashed) crashbits[crash_no[i] >> 6] &= ~(1ull << (crash_no[i] & 63));
+                    if (sh.model->kind == JTB_MODEL_SET) unstep_set(o, &ss);
+                } else if (eligible && sh.model->kind == JTB_MODEL_SET && o.f == JTB_F_ADD) {
+                    // step() never fails for adds; nothing to undo
+                }
+                entry = nxt[entry];
+            } else {
+                // ---- return entry (or end of list): an un-linearized op has returned -> backtrack
+                if (stack.empty()) {
+                    v.valid = JTB_INVALID;
+                    v.witness_ret = max_rj;
+                    return v;
+                }
+                Frame fr = stack.back();
+                stack.pop_back();
+                const int i = fr.op;
+                const Op& o = sh.ops[i];
+                lin[i >> 6] &= ~(1ull << (i & 63));
+                if (o.crashed) {
+                    crashbits[crash_no[i] >> 6] &= ~(1ull << (crash_no[i] & 63));
+                    cls_count[o.cls]--;
+                } else {
+                    n_lin_completed--;
+                }
+                if (sh.model->kind == JTB_MODEL_SET) unstep_set(o, &ss);
+                st = fr.st; rj = fr.rj; mask = fr.mask;
+                relink(2 * i);
+                if (!o.crashed) relink(2 * i + 1);
+                entry = nxt[2 * i];
+            }
+        }
+        return v;
+    }
+};
+
+void fill(const Shard& sh, const Verdict& v, jtb_lin_shard* out) {
+    out->valid = v.valid;
+    out->cause = v.cause;
+    out->configs_explored = v.configs;
+    out->probes = v.probes;
+    out->witness_index = -1;
+    out->previous_ok_index = -1;
+    if (v.valid == JTB_INVALID && v.witness_ret >= 0) {
+        out->witness_index = sh.ops[sh.rets[v.witness_ret]].ret_index;
+        if (v.witness_ret > 0) out->previous_ok_index = sh.ops[sh.rets[v.witness_ret - 1]].ret_index;
+    }
+}
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char* jtbo_last_error(void) { return g_err.c_str(); }
+
+// algo: 0 brute, 1 linear, 2 wgl (full-bitset cache), 3 wgl compact (timed baseline)
+// canon_info: linearize crashed ops of one class (same f/value) in invocation order only
+// n_threads: shards are checked in parallel, one thread per shard at a time (independent/checker)
+int jtbo_check_linearizable(const jtb_history* h, const jtb_model* m, int algo, uint64_t max_configs,
+                            int canon_info, int n_threads, jtb_lin_shard* shards, jtb_lin_result* out) {
+    try {
+        auto t0 = std::chrono::steady_clock::now();
+        std::atomic<int> next{0};
+        std::atomic<bool> failed{false};
+        std::string err;
+        auto work = [&]() {
+            for (;;) {
+                int s = next.fetch_add(1);
+                if (s >= h->n_shards) return;
+                try {
+                    Shard sh = preprocess(h, s, m);
+                    Verdict v;
+                    switch (algo) {
+                    case ALGO_BRUTE: v = Brute(sh).run(); break;
+                    case ALGO_LINEAR: v = Linear(sh, max_configs).run(); break;
+                    case ALGO_WGL: v = WGL(sh, false, canon_info != 0, max_configs).run(); break;
+                    case ALGO_WGL_COMPACT: v = WGL(sh, true, canon_info != 0, max_configs).run(); break;
+                    default: throw std::runtime_error("unknown algo");
+                    }
+                    fill(sh, v, &shards[s]);
+                } catch (const std::exception& e) {
+                    if (!failed.exchange(true)) err = e.what();
+                    return;
+                }
+            }
+        };
+        int nt = std::max(1, std::min(n_threads, (int)h->n_shards));
+        if (nt == 1) work();
+        else {
+            std::vector<std::thread> th;
+            for (int i = 0; i < nt; ++i) th.emplace_back(work);
+            for (auto& t : th) t.join();
+        }
+        if (failed) { g_err = err; return -1; }
+        std::memset(out, 0, sizeof *out);
+        for (int s = 0; s < h->n_shards; ++s) {
+            out->valid = std::max(out->valid, shards[s].valid);
+            out->n_failures += shards[s].valid != JTB_VALID;
+            out->configs_explored += shards[s].configs_explored;
+            out->probes += shards[s].probes;
+        }
+        out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        out->seconds_kernel = out->seconds_total;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+}  // extern "C"
