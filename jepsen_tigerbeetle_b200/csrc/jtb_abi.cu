@@ -1,0 +1,338 @@
+// jtb_abi.cu — C ABI of libjtb_check.so (see include/jtb_check.h): context, device buffers,
+// launchers.  There is no CPU fallback: every check runs its CUDA kernels or returns an error.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "jtb_wgl.cuh"
+#include "jtb_scans.cuh"
+#include "jtb_table_bench.cuh"
+
+using namespace jtb;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct jtb_ctx {
+    int device = 0;
+    jtb_opts opts{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n_sms = 0;
+    std::string err;
+    std::mutex mu;  // a context serialises its calls; use one context per JVM thread for concurrency
+    // cached device buffers (grown on demand, reused across calls)
+    DevBuf table, pool, rows, ops, read_bal, classes, cls_inv, ctrl, found, maxrank, scratch[8];
+    // pinned staging
+    void* pin = nullptr;
+    size_t pin_cap = 0;
+};
+
+namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+int ensure(jtb_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max<size_t>(bytes, 256);
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+template <typename T>
+int upload(jtb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
+    if (ensure(ctx, b, v.size() * sizeof(T) + 64)) return -1;
+    if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+template <int MODEL, int KW>
+int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int32_t init_reg, int grid, size_t smem) {
+    auto k = wgl_search_kernel<MODEL, KW>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, WGL_THREADS, smem, ctx->stream>>>(p, neg_ok, init_reg);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int MODEL>
+int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int32_t init_reg, int grid, size_t smem) {
+    switch (kw) {
+    case 2: return launch_wgl<MODEL, 2>(ctx, p, neg_ok, init_reg, grid, smem);
+    case 4: return launch_wgl<MODEL, 4>(ctx, p, neg_ok, init_reg, grid, smem);
+    case 8: return launch_wgl<MODEL, 8>(ctx, p, neg_ok, init_reg, grid, smem);
+    }
+    ctx->err = "unsupported key width";
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jtb_abi_version(void) { return JTB_ABI_VERSION; }
+
+int jtb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
+    return n;
+}
+
+jtb_ctx* jtb_create(const jtb_opts* opts) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return nullptr;
+    jtb_ctx* ctx = new jtb_ctx();
+    if (opts) ctx->opts = *opts;
+    ctx->device = ctx->opts.device;
+    if (ctx->device < 0 || ctx->device >= n || cudaSetDevice(ctx->device) != cudaSuccess) {
+        delete ctx;
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, ctx->device);
+    ctx->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return nullptr;
+    }
+    return ctx;
+}
+
+void jtb_destroy(jtb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    DevBuf* bufs[] = {&ctx->table, &ctx->pool, &ctx->rows, &ctx->ops, &ctx->read_bal, &ctx->classes,
+                      &ctx->cls_inv, &ctx->ctrl, &ctx->found, &ctx->maxrank};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (DevBuf& b : ctx->scratch)
+        if (b.p) cudaFree(b.p);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* jtb_last_error(const jtb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+
+// -------------------------------------------------------------------------------------------------
+int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, jtb_lin_shard* shards,
+                           jtb_lin_result* out) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const double t_start = now_s();
+    CK(cudaSetDevice(ctx->device));
+    if (m->kind != JTB_MODEL_REGISTER && m->kind != JTB_MODEL_CAS_REGISTER && m->kind != JTB_MODEL_BANK) {
+        ctx->err = "model not supported by the device search";
+        return -2;
+    }
+    Prepared P;
+    if (!prepare(h, m, P)) {
+        ctx->err = "malformed history: " + P.error;
+        return -3;
+    }
+    const int n_shards = h->n_shards;
+    const int KW = P.key_words;
+    const bool bank = m->kind == JTB_MODEL_BANK;
+    const int EW = KW + (bank ? 4 : 0);
+    std::memset(out, 0, sizeof *out);
+    out->key_bytes = KW * 8;
+    for (int s = 0; s < n_shards; ++s) {
+        std::memset(&shards[s], 0, sizeof shards[s]);
+        shards[s].witness_index = shards[s].previous_ok_index = -1;
+        if (P.shard_cause[s]) {
+            shards[s].valid = JTB_UNKNOWN;
+            shards[s].cause = P.shard_cause[s];
+        }
+    }
+    // initial configurations: one per shard that has completed ops
+    std::vector<uint64_t> init_entries;
+    std::vector<int> searchable;
+    for (int s = 0; s < n_shards; ++s) {
+        if (P.shard_cause[s] || P.rank_base[s + 1] == P.rank_base[s]) continue;
+        searchable.push_back(s);
+        std::vector<uint64_t> e(EW, 0);
+        e[0] = KEY_VALID | ((uint64_t)(uint32_t)P.rank_base[s] << 32) |
+               (bank ? 0ull : (uint64_t)(uint32_t)m->init_value);
+        if (bank)
+            for (int i = 0; i < 4; ++i)
+                e[KW + i] = (uint64_t)(uint32_t)m->init_balance[2 * i] |
+                            ((uint64_t)(uint32_t)m->init_balance[2 * i + 1] << 32);
+        init_entries.insert(init_entries.end(), e.begin(), e.end());
+    }
+    double kernel_s = 0;
+    uint64_t configs = 0, probes = 0;
+    if (!searchable.empty()) {
+        if (upload(ctx, ctx->rows, P.rows) || upload(ctx, ctx->ops, P.ops) || upload(ctx, ctx->read_bal, P.read_bal) ||
+            upload(ctx, ctx->classes, P.classes) || upload(ctx, ctx->cls_inv, P.cls_inv_pos))
+            return -1;
+        // work pool
+        const size_t pool_bytes = 1ull << 30;
+        if (ensure(ctx, ctx->pool, pool_bytes)) return -1;
+        const uint64_t pool_cap = pool_bytes / (EW * 8);
+        if (init_entries.size() / EW > pool_cap) { ctx->err = "too many shards for the work pool"; return -1; }
+        if (ensure(ctx, ctx->ctrl, sizeof(Ctrl)) || ensure(ctx, ctx->found, n_shards * sizeof(int)) ||
+            ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
+            return -1;
+        // deque sizing
+        const int cand_rounds = P.S_pad / 32, cls_rounds = (P.max_nc + 31) / 32;
+        const uint32_t worst_push = WGL_WARPS * 32 * (cand_rounds + cls_rounds);
+        uint32_t deque_cap = 512;
+        while (deque_cap < 2 * worst_push) deque_cap <<= 1;
+        const size_t smem = (size_t)deque_cap * EW * 8;
+        if (smem > 200 * 1024) { ctx->err = "too many crashed-op classes for the shared-memory deque"; return -1; }
+        int ctas_per_sm = (int)std::min<size_t>(4, (220 * 1024) / (smem + 1024));
+        ctas_per_sm = std::max(1, ctas_per_sm);
+        int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;
+        // table sizing with escalation on TABLE_FULL
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t max_table = ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)64 << 30;
+        max_table = std::min(max_table, ctx->table.cap + (free_b > ((size_t)2 << 30) ? free_b - ((size_t)2 << 30) : 0));
+        size_t table_bytes = std::min<size_t>(max_table, ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)256 << 20);
+        std::vector<int> h_found(n_shards), h_max(n_shards);
+        Ctrl hc;
+        for (;;) {
+            uint64_t n_slots = 1;
+            while (n_slots * 2 * KW * 8 <= table_bytes) n_slots <<= 1;
+            if (ensure(ctx, ctx->table, n_slots * KW * 8)) return -1;
+            CK(cudaMemsetAsync(ctx->table.p, 0, n_slots * KW * 8, ctx->stream));
+            std::memset(&hc, 0, sizeof hc);
+            hc.pool_top = searchable.size();
+            hc.n_undecided = (int)searchable.size();
+            CK(cudaMemcpyAsync(ctx->ctrl.p, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));
+            for (int s = 0; s < n_shards; ++s) h_max[s] = (int)P.rank_base[s];
+            CK(cudaMemcpyAsync(ctx->maxrank.p, h_max.data(), n_shards * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->pool.p, init_entries.data(), init_entries.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            WglParams p{};
+            p.rows = (const int32_t*)ctx->rows.p;
+            p.ops = (const int4*)ctx->ops.p;
+            p.read_bal = (const int32_t*)ctx->read_bal.p;
+            p.classes = (const ClassRec*)ctx->classes.p;
+            p.cls_inv_pos = (const int32_t*)ctx->cls_inv.p;
+            p.table = (uint64_t*)ctx->table.p;
+            p.slot_mask = n_slots - 1;
+            p.pool = (uint64_t*)ctx->pool.p;
+            p.pool_cap = pool_cap;
+            p.ctrl = (Ctrl*)ctx->ctrl.p;
+            p.shard_found = (int*)ctx->found.p;
+            p.shard_max_rank = (int*)ctx->maxrank.p;
+            p.row_words = P.S_pad + ROW_EXTRA;
+            p.S_pad = P.S_pad;
+            p.n_shards = n_shards;
+            p.max_nc = P.max_nc;
+            const uint64_t load_guard = (uint64_t)(0.70 * (double)n_slots);
+            p.max_configs = load_guard;
+            p.budget_cause = JTB_CAUSE_TABLE_FULL;
+            if (ctx->opts.max_configs && ctx->opts.max_configs <= load_guard) {
+                p.max_configs = ctx->opts.max_configs;
+                p.budget_cause = JTB_CAUSE_BUDGET;
+            }
+            p.time_budget_ns = (unsigned long long)ctx->opts.time_budget_ms * 1000000ull;
+            p.deque_cap = deque_cap;
+            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            int rc;
+            if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, 0, grid, smem);
+            else rc = launch_wgl_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, m->init_value, grid, smem);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CK(cudaMemcpyAsync(&hc, ctx->ctrl.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_found.data(), ctx->found.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_max.data(), ctx->maxrank.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            kernel_s += ms * 1e-3;
+            configs += hc.configs;
+            probes += hc.probes;
+            if (hc.stop == 2 && hc.cause == JTB_CAUSE_TABLE_FULL && table_bytes < max_table) {
+                table_bytes = std::min(max_table, table_bytes * 16);  // escalate and restart
+                continue;
+            }
+            break;
+        }
+        for (int s : searchable) {
+            jtb_lin_shard& r = shards[s];
+            if (h_found[s]) {
+                r.valid = JTB_VALID;
+            } else if (hc.stop == 2) {
+                r.valid = JTB_UNKNOWN;
+                r.cause = hc.cause;
+            } else {
+                r.valid = JTB_INVALID;
+                const int64_t g = h_max[s];
+                r.witness_index = P.ret_index[g];
+                if (g > P.rank_base[s]) r.previous_ok_index = P.ret_index[g - 1];
+            }
+        }
+        if (n_shards == 1) {
+            shards[0].configs_explored = configs;
+            shards[0].probes = probes;
+        }
+    }
+    for (int s = 0; s < n_shards; ++s) {
+        out->valid = std::max(out->valid, shards[s].valid);
+        out->n_failures += shards[s].valid != JTB_VALID;
+    }
+    out->configs_explored = configs;
+    out->probes = probes;
+    out->hbm_bytes_algorithmic = (uint64_t)KW * 8 * (probes + configs);
+    out->seconds_kernel = kernel_s;
+    out->seconds_total = now_s() - t_start;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+int jtb_check_set_full(jtb_ctx* ctx, const jtb_history* h, int linearizable, jtb_setfull_out* out) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    return run_set_full(ctx->stream, ctx->ev0, ctx->ev1, h, linearizable, out, ctx->err);
+}
+
+int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* accounts, int64_t total_amount,
+                          jtb_bank_result* out) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    return run_bank_totals(ctx->stream, ctx->ev0, ctx->ev1, h, accounts, total_amount, out, ctx->err);
+}
+
+int jtb_table_bench(jtb_ctx* ctx, uint64_t n_keys, int variant, int rounds, double* insert_seconds,
+                    double* probe_seconds, uint64_t* found) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    size_t table_bytes = ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)8 << 30;
+    uint64_t n_slots = 1;
+    while (n_slots * 2 * 16 <= table_bytes) n_slots <<= 1;
+    if (ensure(ctx, ctx->table, n_slots * 16)) return -1;
+    return run_table_bench(ctx->stream, ctx->ev0, ctx->ev1, (uint64_t*)ctx->table.p, n_slots, n_keys, variant, rounds,
+                           ctx->n_sms, insert_seconds, probe_seconds, found, ctx->err);
+}
+
+}  // extern "C"

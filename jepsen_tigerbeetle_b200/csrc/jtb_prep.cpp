@@ -1,0 +1,273 @@
+// jtb_prep.cpp — see jtb_prep.h.  Host-side O(events) preparation: pairing, return ranks, open-op
+// slots (interval colouring), crashed-op classes, frontier rows, per-model op resolution.
+#include "jtb_prep.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <unordered_map>
+
+namespace jtb {
+namespace {
+
+struct HOp {
+    int inv_pos, ret_pos;      // ret_pos == INT_MAX for crashed ops
+    int inv_ev, ret_ev;        // event numbers (absolute) of the invoke / completion, -1 if none
+    bool crashed, dropped;
+    int slot, rank;            // completed ops
+    int cls;                   // crashed ops
+};
+
+struct ShardTmp {
+    std::vector<HOp> ops;            // kept ops, invocation order
+    std::vector<int> rets;           // completed op ids in return order
+    int S = 0;
+    std::vector<std::vector<int>> cls_members;
+    std::vector<int> cls_rep;        // representative op of each class
+    bool too_wide = false;
+};
+
+inline int acct_slot(const jtb_model* m, int32_t id) {
+    for (int i = 0; i < m->n_accounts; ++i)
+        if (m->account_ids[i] == id) return i;
+    return -1;
+}
+
+// Resolve one op into its device record.  `ev` is the event whose value the op carries (the :ok
+// completion for completed ops, the invoke for crashed ones).
+OpRec resolve(const jtb_history* h, const jtb_model* m, int64_t ev, Prepared& out) {
+    OpRec r{0, 0, 0, 0};
+    const int f = h->f[ev];
+    r.x = f;
+    switch (m->kind) {
+    case JTB_MODEL_REGISTER:
+    case JTB_MODEL_CAS_REGISTER:
+        r.y = h->a[ev];
+        r.z = h->b[ev];
+        if (f == JTB_F_CAS && m->kind != JTB_MODEL_CAS_REGISTER) r.x |= OP_IMPOSSIBLE;
+        if (f != JTB_F_READ && f != JTB_F_WRITE && f != JTB_F_CAS) r.x |= OP_IMPOSSIBLE;
+        break;
+    case JTB_MODEL_BANK:
+        if (f == JTB_F_TRANSFER) {
+            const int d = acct_slot(m, h->b[ev]), c = acct_slot(m, h->c[ev]);
+            r.y = h->a[ev];
+            r.z = d;
+            r.w = c;
+            if (d < 0 || c < 0) r.x |= OP_IMPOSSIBLE;
+        } else if (f == JTB_F_READ) {
+            int32_t bal[JTB_MAX_ACCOUNTS] = {0};
+            int care = 0;
+            const int n = h->payload_len[ev];
+            if (n < 0) r.x |= OP_IMPOSSIBLE;  // :ok read of nil
+            const int32_t* pl = h->payload + h->payload_off[ev];
+            for (int i = 0; i + 1 < n; i += 2) {
+                const int sl = acct_slot(m, pl[i]);
+                if (sl < 0 || pl[i + 1] == JTB_NIL) { r.x |= OP_IMPOSSIBLE; continue; }
+                if ((care >> sl & 1) && bal[sl] != pl[i + 1]) r.x |= OP_IMPOSSIBLE;
+                care |= 1 << sl;
+                bal[sl] = pl[i + 1];
+            }
+            r.y = care;
+            r.z = (int32_t)(out.read_bal.size() / JTB_MAX_ACCOUNTS);
+            out.read_bal.insert(out.read_bal.end(), bal, bal + JTB_MAX_ACCOUNTS);
+        } else {
+            r.x |= OP_IMPOSSIBLE;
+        }
+        break;
+    default:
+        r.x |= OP_IMPOSSIBLE;
+    }
+    return r;
+}
+
+}  // namespace
+
+bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
+    out = Prepared();
+    out.model = m->kind;
+    const int n_shards = h->n_shards;
+    std::vector<ShardTmp> tmp(n_shards);
+    out.shard_cause.assign(n_shards, JTB_CAUSE_NONE);
+    out.max_classes.assign(n_shards, 0);
+    if (m->kind == JTB_MODEL_BANK && (m->n_accounts < 1 || m->n_accounts > JTB_MAX_ACCOUNTS)) {
+        out.error = "bank model needs 1..8 accounts";
+        return false;
+    }
+    // ---- pass 1: pairing, ranks, slots, classes ---------------------------------------------
+    int S_max = 1;
+    for (int s = 0; s < n_shards; ++s) {
+        ShardTmp& t = tmp[s];
+        std::unordered_map<int32_t, int> open;
+        std::vector<HOp> all;
+        int pos = 0;
+        for (int64_t e = h->shard_off[s]; e < h->shard_off[s + 1]; ++e) {
+            const int32_t p = h->process[e];
+            if (p < 0) continue;
+            if (h->type[e] == JTB_T_INVOKE) {
+                if (open.count(p)) { out.error = "process invoked twice without completing"; return false; }
+                open[p] = (int)all.size();
+                all.push_back(HOp{pos++, INT_MAX, (int)e, -1, false, false, -1, -1, -1});
+            } else {
+                auto it = open.find(p);
+                if (it == open.end()) { out.error = "completion without invocation"; return false; }
+                HOp& o = all[it->second];
+                open.erase(it);
+                o.ret_ev = (int)e;
+                if (h->type[e] == JTB_T_OK) o.ret_pos = pos;
+                else if (h->type[e] == JTB_T_FAIL) o.dropped = true;
+                else o.crashed = true;
+                ++pos;
+            }
+        }
+        for (auto& kv : open) all[kv.second].crashed = true;
+        for (auto& o : all) {
+            if (o.dropped) continue;
+            if (o.crashed && h->f[o.inv_ev] == JTB_F_READ) continue;
+            t.ops.push_back(o);
+        }
+        // return ranks
+        for (int i = 0; i < (int)t.ops.size(); ++i)
+            if (!t.ops[i].crashed) t.rets.push_back(i);
+        std::sort(t.rets.begin(), t.rets.end(),
+                  [&](int x, int y) { return t.ops[x].ret_pos < t.ops[y].ret_pos; });
+        for (int j = 0; j < (int)t.rets.size(); ++j) t.ops[t.rets[j]].rank = j;
+        // slots: sweep in position order; ops are already sorted by inv_pos, returns by rank
+        {
+            uint64_t free_lo = ~0ull;  // bit set = slot free (slots 0..63)
+            size_t ri = 0;
+            int S = 0;
+            for (int i = 0; i < (int)t.ops.size() && !t.too_wide; ++i) {
+                HOp& o = t.ops[i];
+                if (o.crashed) continue;
+                while (ri < t.rets.size() && t.ops[t.rets[ri]].ret_pos < o.inv_pos) {
+                    free_lo |= 1ull << t.ops[t.rets[ri]].slot;
+                    ++ri;
+                }
+                if (!free_lo) { t.too_wide = true; break; }
+                const int sl = __builtin_ctzll(free_lo);
+                free_lo &= ~(1ull << sl);
+                o.slot = sl;
+                S = std::max(S, sl + 1);
+            }
+            t.S = S;
+        }
+        if (t.too_wide) {
+            out.shard_cause[s] = JTB_CAUSE_TOO_WIDE;
+            t.rets.clear();
+            continue;
+        }
+        S_max = std::max(S_max, t.S);
+        // crashed-op classes: same (f, a, b, c)
+        std::map<std::tuple<int, int32_t, int32_t, int32_t>, int> cls;
+        for (int i = 0; i < (int)t.ops.size(); ++i) {
+            HOp& o = t.ops[i];
+            if (!o.crashed) continue;
+            const int64_t e = o.inv_ev;
+            auto key = std::make_tuple((int)h->f[e], h->a[e], h->b[e], h->c[e]);
+            auto it = cls.find(key);
+            if (it == cls.end()) {
+                it = cls.emplace(key, (int)cls.size()).first;
+                t.cls_members.emplace_back();
+                t.cls_rep.push_back(i);
+            }
+            o.cls = it->second;
+            t.cls_members[o.cls].push_back(i);
+        }
+        out.max_classes[s] = (int)t.cls_members.size();
+        out.max_nc = std::max(out.max_nc, out.max_classes[s]);
+    }
+    out.S_pad = S_max <= 32 ? 32 : 64;
+    const int S_bits = S_max;
+    // ---- pass 2: key layout (count fields of crashed-op classes) -----------------------------
+    // word 0: valid | global rank | register state ; word 1: open-op mask in bits [0, S_bits),
+    // class counts packed above it and into words 2.. (a field never straddles a word).
+    int key_words = 2;
+    std::vector<std::vector<std::pair<int, int>>> field(n_shards);  // (word, shift|width<<8)
+    for (int s = 0; s < n_shards; ++s) {
+        ShardTmp& t = tmp[s];
+        if (out.shard_cause[s]) continue;
+        int word = 1, bit = S_bits;
+        for (auto& mem : t.cls_members) {
+            int width = 1;
+            while ((1 << width) <= (int)mem.size()) ++width;  // counts 0..n need ceil(log2(n+1)) bits
+            if (bit + width > 64) { ++word; bit = 0; }
+            field[s].push_back({word, bit | width << 8});
+            bit += width;
+        }
+        int need = word + 1;
+        int kw = need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 0;
+        if (kw == 0) {
+            out.shard_cause[s] = JTB_CAUSE_TOO_WIDE;
+            t.rets.clear();
+            field[s].clear();
+            continue;
+        }
+        key_words = std::max(key_words, kw);
+    }
+    out.key_words = key_words;
+    // ---- pass 3: tables -----------------------------------------------------------------------
+    const int RW = out.S_pad + ROW_EXTRA;
+    out.rank_base.assign(n_shards + 1, 0);
+    for (int s = 0; s < n_shards; ++s) out.rank_base[s + 1] = out.rank_base[s] + (int64_t)tmp[s].rets.size();
+    out.n_ranks = out.rank_base[n_shards];
+    if (out.n_ranks >= (1ll << 31) - 64) { out.error = "history too large"; return false; }
+    out.rows.assign((size_t)out.n_ranks * RW, -1);
+    out.ret_index.assign((size_t)out.n_ranks, -1);
+    for (int s = 0; s < n_shards; ++s) {
+        ShardTmp& t = tmp[s];
+        const int R = (int)t.rets.size();
+        if (R == 0) continue;
+        const int64_t base = out.rank_base[s];
+        const int32_t op_base = (int32_t)out.ops.size();
+        // op records (completed ops only live in the table; crashed ones live in class records)
+        std::vector<int32_t> gid(t.ops.size(), -1);
+        for (int i = 0; i < (int)t.ops.size(); ++i) {
+            if (t.ops[i].crashed) continue;
+            gid[i] = (int32_t)out.ops.size();
+            out.ops.push_back(resolve(h, m, t.ops[i].ret_ev, out));
+        }
+        (void)op_base;
+        // class records
+        const int32_t cls_base = (int32_t)out.classes.size();
+        for (size_t c = 0; c < t.cls_members.size(); ++c) {
+            ClassRec cr;
+            cr.op = resolve(h, m, t.ops[t.cls_rep[c]].inv_ev, out);
+            cr.first = (int32_t)out.cls_inv_pos.size();
+            cr.n = (int32_t)t.cls_members[c].size();
+            cr.word = field[s][c].first;
+            cr.shift_width = field[s][c].second;
+            for (int i : t.cls_members[c]) out.cls_inv_pos.push_back(t.ops[i].inv_pos);
+            out.classes.push_back(cr);
+        }
+        // rows: sweep invocations and returns in position order
+        std::vector<int32_t> cur(out.S_pad, -1);
+        size_t oi = 0;
+        for (int j = 0; j < R; ++j) {
+            const HOp& ro = t.ops[t.rets[j]];
+            while (oi < t.ops.size() && t.ops[oi].inv_pos < ro.ret_pos) {
+                if (!t.ops[oi].crashed) cur[t.ops[oi].slot] = gid[oi];
+                ++oi;
+            }
+            int32_t* row = &out.rows[(size_t)(base + j) * RW];
+            std::memcpy(row, cur.data(), out.S_pad * sizeof(int32_t));
+            uint8_t* nxt = reinterpret_cast<uint8_t*>(row + out.S_pad);
+            for (int k = 0; k < 32; ++k)
+                nxt[k] = (j + 1 + k < R) ? (uint8_t)t.ops[t.rets[j + 1 + k]].slot : (uint8_t)0xFF;
+            row[out.S_pad + 8] = ro.ret_pos;
+            row[out.S_pad + 9] = s;
+            row[out.S_pad + 10] = (int32_t)(base + R);
+            row[out.S_pad + 11] = cls_base;
+            row[out.S_pad + 12] = (int32_t)t.cls_members.size();
+            row[out.S_pad + 13] = ro.slot;
+            row[out.S_pad + 14] = 0;
+            row[out.S_pad + 15] = 0;
+            out.ret_index[base + j] = h->index[ro.ret_ev];
+            cur[ro.slot] = -1;  // the op has returned
+        }
+    }
+    return true;
+}
+
+}  // namespace jtb

@@ -1,0 +1,75 @@
+// jtb_prep.h — host-side preparation of a flattened history for the device search.
+//
+// Product code (libjtb_check.so).  Independent of oracle/ (which is test infrastructure).
+// Follows knossos.history/{complete, without-failures, pair-index}:
+//   client ops only; invoke paired with completion by :process; :fail pairs removed; :info ops stay
+//   open forever; crashed reads dropped.  Reference consumers of the same pairing:
+//   src/tigerbeetle/tests/ledger.clj:206 (history/unmatched-invokes), checker/perf.clj:617,623.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/jtb_check.h"
+
+namespace jtb {
+
+// One op as the device sees it (16 B, loaded as int4).
+//   x = f | flags<<8   (flag bit 8: impossible — can never be linearized)
+//   register/cas: y = value / cas-old, z = cas-new
+//   bank transfer: y = amount, z = debit slot, w = credit slot
+//   bank read:     y = care mask over account slots, z = index into read_bal (8 int32 each)
+//   set add:       y = dense element id
+//   set read:      y = offset into set_need (per (read, frontier) need/care masks), z = first rank, w = last rank
+struct OpRec {
+    int32_t x, y, z, w;
+};
+constexpr int OP_IMPOSSIBLE = 1 << 8;
+
+// Crashed-op equivalence class (same f and value): members are linearized in invocation order only,
+// so a config records just how many of the class it has consumed (a count field inside the key).
+struct ClassRec {
+    OpRec op;
+    int32_t first;   // offset of the class' members in cls_inv_pos
+    int32_t n;       // number of members
+    int32_t word;    // key word holding the count
+    int32_t shift_width;  // shift | width << 8
+};
+
+// Row of the frontier table: everything a warp needs to expand a config whose first un-linearized
+// return is global rank gj.  int32 words:
+//   [0, S_pad)            global op id occupying each open-op slot at that return event (-1 none)
+//   [S_pad, S_pad+8)      slots (u8) of the next 32 returns gj+1 .. gj+32 (0xFF beyond the shard end)
+//   [S_pad+8]             position of the return event (for crashed-op eligibility)
+//   [S_pad+9]             shard id
+//   [S_pad+10]            global rank one past the shard's last return (success when reached)
+//   [S_pad+11]            first class record of the shard
+//   [S_pad+12]            number of classes of the shard
+//   [S_pad+13]            slot of this rank's own op
+//   [S_pad+14..15]        pad
+constexpr int ROW_EXTRA = 16;
+
+struct Prepared {
+    int S_pad = 32;          // 32 or 64
+    int key_words = 2;       // 64-bit words per key: 2, 4 or 8
+    int model = 0;
+    int64_t n_ranks = 0;     // total completed ops over all searchable shards
+    std::vector<int32_t> rows;        // n_ranks * (S_pad + ROW_EXTRA)
+    std::vector<OpRec> ops;           // global op table
+    std::vector<int32_t> read_bal;    // bank: 8 per read
+    std::vector<uint64_t> set_need;   // set: (need, care) pairs
+    std::vector<ClassRec> classes;
+    std::vector<int32_t> cls_inv_pos;
+    // per shard (host side)
+    std::vector<int64_t> rank_base;   // [n_shards+1]
+    std::vector<int32_t> ret_index;   // [n_ranks] :index of each return completion
+    std::vector<int32_t> shard_cause; // JTB_CAUSE_* decided on the host (too wide), else 0
+    std::vector<int32_t> max_classes; // classes per shard
+    int max_nc = 0;                   // max classes in any shard
+    std::string error;
+};
+
+// Returns false (and sets out.error) on malformed histories.
+bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out);
+
+}  // namespace jtb

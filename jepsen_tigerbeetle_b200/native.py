@@ -1,0 +1,182 @@
+"""ctypes binding of the product library `libjtb_check.so` (C ABI in include/jtb_check.h).
+
+This is the same boundary a JVM host binds through JNI.  There is NO fallback:
+if the CUDA library is missing or no device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+from . import abi
+from .history import CHistory, CModel, FlatHistory, as_c_history
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjtb_check.so")
+CSRC = os.path.join(_HERE, "csrc")
+_SOURCES = ["jtb_abi.cu", "jtb_prep.cpp"]
+_DEPS = _SOURCES + ["jtb_prep.h", "jtb_wgl.cuh", "jtb_scans.cuh", "jtb_table_bench.cuh"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
+           "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
+           "jtb_table_bench"]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    deps = [os.path.join(CSRC, f) for f in _DEPS]
+    deps.append(os.path.join(_HERE, "..", "include", "jtb_check.h"))
+    stale = (not os.path.exists(LIB_PATH)
+             or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps))
+    if force or stale:
+        cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, f) for f in _SOURCES]
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                                  "g.build()'` (there is no CPU fallback)")
+            L = C.CDLL(LIB_PATH)
+            L.jtb_abi_version.restype = C.c_int
+            L.jtb_device_count.restype = C.c_int
+            L.jtb_create.restype = C.c_void_p
+            L.jtb_create.argtypes = [C.c_void_p]
+            L.jtb_destroy.argtypes = [C.c_void_p]
+            L.jtb_last_error.restype = C.c_char_p
+            L.jtb_last_error.argtypes = [C.c_void_p]
+            L.jtb_check_linearizable.argtypes = [C.c_void_p] * 5
+            L.jtb_check_set_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.jtb_check_bank_totals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+            L.jtb_table_bench.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+            if L.jtb_abi_version() != abi.ABI_VERSION:
+                raise NativeError("ABI version mismatch between libjtb_check.so and abi.py")
+            _lib = L
+    return _lib
+
+
+class Context:
+    """One checker context = one CUDA device + stream + cached device buffers (`jtb_ctx`)."""
+
+    def __init__(self, device: int = 0, table_bytes: int = 0, max_configs: int = 0,
+                 time_budget_ms: int = 0, search_ctas: int = 0) -> None:
+        L = lib()
+        opts = abi.COpts(device, 0, table_bytes, max_configs, time_budget_ms, search_ctas)
+        self._h = L.jtb_create(C.byref(opts))
+        if not self._h:
+            raise NativeError("jtb_create failed: no CUDA device available (no CPU fallback)")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().jtb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _err(self) -> str:
+        return lib().jtb_last_error(self._h).decode()
+
+    # ---- hot path A9 ----------------------------------------------------------------------------
+    def check_linearizable(self, h: FlatHistory, model: CModel) -> dict:
+        ch = as_c_history(h)
+        shards = (abi.CLinShard * h.n_shards)()
+        res = abi.CLinResult()
+        rc = lib().jtb_check_linearizable(self._h, C.addressof(ch), C.addressof(model),
+                                          C.addressof(shards), C.addressof(res))
+        if rc != 0:
+            raise NativeError(f"jtb_check_linearizable rc={rc}: {self._err()}")
+        return {
+            "valid": res.valid, "n_failures": res.n_failures, "configs": res.configs_explored,
+            "probes": res.probes, "hbm_bytes_algorithmic": res.hbm_bytes_algorithmic,
+            "key_bytes": res.key_bytes, "seconds_kernel": res.seconds_kernel,
+            "seconds_total": res.seconds_total,
+            "shards": [{"valid": s.valid, "witness_index": s.witness_index,
+                        "previous_ok_index": s.previous_ok_index, "cause": s.cause,
+                        "configs": s.configs_explored, "probes": s.probes} for s in shards],
+        }
+
+    # ---- hot path A4 ----------------------------------------------------------------------------
+    def check_set_full(self, h: FlatHistory, linearizable: bool = True) -> dict:
+        ch = as_c_history(h)
+        shards = (abi.CSetFullShard * h.n_shards)()
+        cap = int(np.count_nonzero((h.f == 3) & (h.type == 0))) + 1
+        elem_off = np.zeros(h.n_shards + 1, np.int64)
+        elem_id = np.zeros(cap, np.int32)
+        elem_outcome = np.zeros(cap, np.uint8)
+        elem_lat = np.zeros(cap, np.int64)
+        elem_dup = np.zeros(cap, np.int32)
+        out = abi.CSetFullOut(C.cast(shards, C.c_void_p), cap, elem_off.ctypes.data,
+                              elem_id.ctypes.data, elem_outcome.ctypes.data, elem_lat.ctypes.data,
+                              elem_dup.ctypes.data)
+        rc = lib().jtb_check_set_full(self._h, C.addressof(ch), int(linearizable), C.addressof(out))
+        if rc != 0:
+            raise NativeError(f"jtb_check_set_full rc={rc}: {self._err()}")
+        n = int(elem_off[-1])
+        fields = ("valid", "attempt_count", "stable_count", "lost_count", "never_read_count",
+                  "stale_count", "duplicated_count", "stable_latency_max_ms", "lost_latency_max_ms")
+        return {
+            "valid": out.valid, "n_failures": out.n_failures, "seconds": out.seconds_total,
+            "seconds_kernel": out.seconds_kernel,
+            "shards": [{f: getattr(s, f) for f in fields} for s in shards],
+            "elem_off": elem_off.copy(), "elem_id": elem_id[:n].copy(),
+            "elem_outcome": elem_outcome[:n].copy(), "elem_latency_ms": elem_lat[:n].copy(),
+            "elem_dup_count": elem_dup[:n].copy(),
+        }
+
+    # ---- hot path A8 ----------------------------------------------------------------------------
+    def check_bank_totals(self, h: FlatHistory, model: CModel, total_amount: int = 0) -> dict:
+        ch = as_c_history(h)
+        res = abi.CBankResult()
+        rc = lib().jtb_check_bank_totals(self._h, C.addressof(ch), C.addressof(model),
+                                         C.c_int64(total_amount), C.addressof(res))
+        if rc != 0:
+            raise NativeError(f"jtb_check_bank_totals rc={rc}: {self._err()}")
+        return {
+            "valid": res.valid, "read_count": res.read_count, "error_count": res.error_count,
+            "first_error_index": res.first_error_index, "first_error_type": res.first_error_type,
+            "count_by_type": list(res.count_by_type),
+            "first_index_by_type": list(res.first_index_by_type),
+            "last_index_by_type": list(res.last_index_by_type),
+            "worst_index_by_type": list(res.worst_index_by_type),
+            "lowest_total": res.lowest_total, "highest_total": res.highest_total,
+            "lowest_index": res.lowest_index, "highest_index": res.highest_index,
+            "seconds": res.seconds_total, "seconds_kernel": res.seconds_kernel,
+        }
+
+    # ---- K2 microbenchmark ----------------------------------------------------------------------
+    def table_bench(self, n_keys: int, variant: int = 0, rounds: int = 3) -> dict:
+        ins, prb, found = C.c_double(), C.c_double(), C.c_uint64()
+        rc = lib().jtb_table_bench(self._h, n_keys, variant, rounds, C.addressof(ins),
+                                   C.addressof(prb), C.addressof(found))
+        if rc != 0:
+            raise NativeError(f"jtb_table_bench rc={rc}: {self._err()}")
+        return {"insert_seconds": ins.value, "probe_seconds": prb.value, "found": found.value,
+                "n_keys": n_keys, "rounds": rounds, "variant": variant}
+
+
+def device_count() -> int:
+    return lib().jtb_device_count()

@@ -1,0 +1,162 @@
+"""GPU parity tests proper: every call goes through the C ABI (libjtb_check.so) and is compared with
+the CPU oracle on the same seeded inputs — bit-exact verdict, witness index and (for exhaustive
+searches) the number of distinct configurations."""
+import numpy as np
+import pytest
+
+import kat
+from jepsen_tigerbeetle_b200 import history as H
+from jepsen_tigerbeetle_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def model_for(name, **kw):
+    if name == "register":
+        return H.make_model(H.MODEL_REGISTER)
+    if name == "cas-register":
+        return H.make_model(H.MODEL_CAS_REGISTER)
+    if name == "set":
+        return H.make_model(H.MODEL_SET)
+    return H.make_model(H.MODEL_BANK, accounts=range(1, 9), **kw)
+
+
+def same_verdict(g, o):
+    assert g["valid"] == o["valid"], (g, o)
+    for gs, os_ in zip(g["shards"], o["shards"]):
+        assert gs["valid"] == os_["valid"]
+        assert gs["witness_index"] == os_["witness_index"], (gs, os_)
+        assert gs["previous_ok_index"] == os_["previous_ok_index"], (gs, os_)
+
+
+GPU_LIN_KATS = [k for k in kat.ALL_LIN_KATS if k[1] != "set"]
+
+
+@pytest.mark.parametrize("name,model,text,expect,witness", GPU_LIN_KATS, ids=[k[0] for k in GPU_LIN_KATS])
+def test_kats(gpu_ctx, oracle_mod, name, model, text, expect, witness):
+    h = H.flatten_ops(kat.ops(text), model)
+    g = gpu_ctx.check_linearizable(h, model_for(model))
+    assert g["valid"] == expect
+    if expect == H.INVALID and witness is not None:
+        assert g["shards"][0]["witness_index"] == witness
+    same_verdict(g, oracle_mod.check_linearizable(h, model_for(model), 3))
+
+
+def test_bank_negative_balances_forbidden(gpu_ctx):
+    h = H.flatten_ops(kat.ops("0:inv transfer t(1 2 3), 0:ok transfer t(1 2 3)"), "bank")
+    assert gpu_ctx.check_linearizable(h, model_for("bank", negative_balances_ok=False))["valid"] == H.INVALID
+    assert gpu_ctx.check_linearizable(h, model_for("bank"))["valid"] == H.VALID
+
+
+@pytest.mark.parametrize("model", ["register", "cas-register", "bank"])
+def test_random_small(gpu_ctx, oracle_mod, model):
+    for seed in range(40):
+        spec = synth.SynthSpec(model, n_ops=60, n_clients=4, seed=seed, p_info=0.1 if seed % 2 else 0.0,
+                               stale_read=seed % 3 != 0, stale_by=3 + seed % 5, n_values=3)
+        h = synth.generate(spec)
+        m = model_for(model)
+        g = gpu_ctx.check_linearizable(h, m)
+        o = oracle_mod.check_linearizable(h, m, 3)
+        same_verdict(g, o)
+        if o["valid"] == H.INVALID:
+            assert g["configs"] == o["configs"], (model, seed)
+
+
+@pytest.mark.parametrize("p_info", [0.0, 0.05])
+@pytest.mark.parametrize("stale", [False, True])
+def test_config_c2(gpu_ctx, oracle_mod, p_info, stale):
+    """BASELINE config #2: 1k-op cas-register history, 16 clients."""
+    for seed in (1, 2, 3):
+        h = synth.config_c2(seed=seed, p_info=p_info, stale_read=stale)
+        m = model_for("cas-register")
+        g = gpu_ctx.check_linearizable(h, m)
+        o = oracle_mod.check_linearizable(h, m, 3)
+        same_verdict(g, o)
+        if o["valid"] == H.INVALID:
+            assert g["configs"] == o["configs"]
+
+
+@pytest.mark.parametrize("stale", [False, True])
+def test_config_c3_lite(gpu_ctx, oracle_mod, stale):
+    """BASELINE config #3 shape at a size the oracle finishes in seconds: bank, 32 clients."""
+    h = synth.generate(synth.SynthSpec("bank", 10000, 32, 1, tau_think_ns=20e6, stale_read=stale))
+    m = model_for("bank")
+    g = gpu_ctx.check_linearizable(h, m)
+    o = oracle_mod.check_linearizable(h, m, 3)
+    same_verdict(g, o)
+    if stale:
+        assert o["valid"] == H.INVALID and g["configs"] == o["configs"]
+
+
+def test_bank_with_crashed_transfers(gpu_ctx, oracle_mod):
+    for seed in (1, 2):
+        h = synth.generate(synth.SynthSpec("bank", 600, 8, seed, p_info=0.05, tau_think_ns=10e6,
+                                           stale_read=seed == 2))
+        m = model_for("bank")
+        g = gpu_ctx.check_linearizable(h, m)
+        o = oracle_mod.check_linearizable(h, m, 3)
+        same_verdict(g, o)
+
+
+def test_multi_shard(gpu_ctx, oracle_mod):
+    """independent keys: per-key verdicts, merged with merge-valid; one poisoned key flips the verdict."""
+    h = synth.generate(synth.SynthSpec("cas-register", 4000, 64, 5, p_info=0.1, n_keys=8, grouped_keys=True))
+    m = model_for("cas-register")
+    g = gpu_ctx.check_linearizable(h, m)
+    o = oracle_mod.check_linearizable(h, m, 3, n_threads=4)
+    same_verdict(g, o)
+    assert g["valid"] == H.VALID
+    h = synth.generate(synth.SynthSpec("cas-register", 4000, 64, 5, p_info=0.1, n_keys=8, grouped_keys=True,
+                                       stale_read=True))
+    g = gpu_ctx.check_linearizable(h, m)
+    o = oracle_mod.check_linearizable(h, m, 3, n_threads=4)
+    same_verdict(g, o)
+    assert g["n_failures"] == o["n_failures"]
+
+
+def test_budget_gives_unknown(oracle_mod):
+    from jepsen_tigerbeetle_b200 import native
+    h = synth.generate(synth.SynthSpec("bank", 10000, 32, 1, tau_think_ns=20e6, stale_read=True))
+    with native.Context(max_configs=20000) as ctx:
+        g = ctx.check_linearizable(h, model_for("bank"))
+    assert g["valid"] == H.UNKNOWN and g["shards"][0]["cause"] == 2
+
+
+# ---- scans -------------------------------------------------------------------------------------------
+def sf_equal(g, o):
+    assert g["valid"] == o["valid"]
+    assert g["shards"] == o["shards"]
+    for k in ("elem_off", "elem_id", "elem_outcome", "elem_latency_ms", "elem_dup_count"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+def test_set_full_c1(gpu_ctx, oracle_mod):
+    for seed in (1, 2, 3):
+        h = synth.config_c1(seed=seed)
+        for lin in (True, False):
+            sf_equal(gpu_ctx.check_set_full(h, lin), oracle_mod.check_set_full(h, lin))
+
+
+def test_set_full_multi_key_with_info(gpu_ctx, oracle_mod):
+    h = synth.config_c4(seed=2, n_keys=8, n_ops=8000)
+    sf_equal(gpu_ctx.check_set_full(h), oracle_mod.check_set_full(h))
+
+
+def test_bank_totals(gpu_ctx, oracle_mod):
+    h = synth.generate(synth.SynthSpec("bank", 3000, 16, 4, tau_think_ns=20e6))
+    m = model_for("bank")
+    g, o = gpu_ctx.check_bank_totals(h, m, 0), oracle_mod.check_bank_totals(h, m, 0)
+    for k in g:
+        if not k.startswith("seconds"):
+            assert g[k] == o[k], k
+    # corrupt some reads
+    rng = np.random.default_rng(0)
+    idx = np.flatnonzero(h.payload_len > 0)
+    for e in rng.choice(idx, 40, replace=False):
+        h.payload[h.payload_off[e] + 1 + 2 * int(rng.integers(0, 8))] += int(rng.integers(-9, 9))
+    for neg_ok in (True, False):
+        m = model_for("bank", negative_balances_ok=neg_ok)
+        g, o = gpu_ctx.check_bank_totals(h, m, 0), oracle_mod.check_bank_totals(h, m, 0)
+        for k in g:
+            if not k.startswith("seconds"):
+                assert g[k] == o[k], (k, neg_ok)

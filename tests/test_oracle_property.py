@@ -1,0 +1,94 @@
+"""Cross-checks between the four independent CPU deciders (CPU only).  brute == linear == wgl ==
+wgl-compact on tiny histories; linear == wgl == wgl-compact on medium ones; metamorphic properties."""
+import numpy as np
+import pytest
+
+from jepsen_tigerbeetle_b200 import history as H
+from jepsen_tigerbeetle_b200 import synth
+
+MODELS = {
+    "register": lambda: H.make_model(H.MODEL_REGISTER),
+    "cas-register": lambda: H.make_model(H.MODEL_CAS_REGISTER),
+    "set": lambda: H.make_model(H.MODEL_SET),
+    "bank": lambda: H.make_model(H.MODEL_BANK, accounts=range(1, 9)),
+}
+
+
+def verdict(r):
+    return (r["valid"], r["shards"][0]["witness_index"])
+
+
+@pytest.mark.parametrize("model", list(MODELS))
+def test_tiny_all_four_agree(oracle_mod, model):
+    n_invalid = 0
+    for seed in range(60):
+        spec = synth.SynthSpec(model, n_ops=7, n_clients=3, seed=seed, p_info=0.15 if seed % 2 else 0.0,
+                               stale_read=seed % 3 != 0, stale_by=2 + seed % 3, n_values=3, n_accounts=3)
+        h = synth.generate(spec)
+        m = MODELS[model]() if model != "bank" else H.make_model(H.MODEL_BANK, accounts=range(1, 4))
+        rs = [verdict(oracle_mod.check_linearizable(h, m, a)) for a in (0, 1, 2, 3)]
+        assert rs[0] == rs[1] == rs[2] == rs[3], (model, seed, rs)
+        n_invalid += rs[0][0] == H.INVALID
+    assert n_invalid > 0  # the mutation does produce invalid histories
+
+
+@pytest.mark.parametrize("model", list(MODELS))
+def test_medium_three_agree(oracle_mod, model):
+    for seed in range(8):
+        spec = synth.SynthSpec(model, n_ops=300, n_clients=5, seed=100 + seed, p_info=0.03 if seed % 2 else 0.0,
+                               stale_read=seed % 2 == 0, n_values=4, tau_think_ns=5e6)
+        h = synth.generate(spec)
+        m = MODELS[model]()
+        rs = [verdict(oracle_mod.check_linearizable(h, m, a)) for a in (1, 2, 3)]
+        assert rs[0] == rs[1] == rs[2], (model, seed, rs)
+
+
+def test_canonical_crashed_classes_do_not_change_verdict(oracle_mod):
+    for seed in range(12):
+        spec = synth.SynthSpec("cas-register", n_ops=120, n_clients=4, seed=500 + seed, p_info=0.3,
+                               stale_read=seed % 2 == 0, n_values=3)
+        h = synth.generate(spec)
+        m = MODELS["cas-register"]()
+        a = oracle_mod.check_linearizable(h, m, 3, canon_info=True)
+        b = oracle_mod.check_linearizable(h, m, 3, canon_info=False)
+        c = oracle_mod.check_linearizable(h, m, 2, canon_info=False)
+        assert verdict(a) == verdict(b) == verdict(c)
+        assert a["configs"] <= b["configs"]
+
+
+def test_exhaustive_count_is_order_independent(oracle_mod):
+    # for an INVALID history both WGL caches hold exactly the reachable configs
+    spec = synth.SynthSpec("bank", n_ops=400, n_clients=6, seed=7, stale_read=True, tau_think_ns=2e6)
+    h = synth.generate(spec)
+    m = MODELS["bank"]()
+    a = oracle_mod.check_linearizable(h, m, 2)
+    b = oracle_mod.check_linearizable(h, m, 3)
+    assert a["valid"] == b["valid"] == H.INVALID
+    assert a["configs"] == b["configs"]
+
+
+def test_metamorphic_process_relabel_and_time_dilation(oracle_mod):
+    spec = synth.SynthSpec("cas-register", n_ops=200, n_clients=5, seed=11, stale_read=True)
+    h = synth.generate(spec)
+    m = MODELS["cas-register"]()
+    base = verdict(oracle_mod.check_linearizable(h, m, 3))
+    h2 = synth.generate(spec)
+    h2.process[:] = (h2.process * 7 + 3).astype(np.int32)   # injective relabelling
+    h2.time_ns[:] = h2.time_ns * 3 + 17
+    assert verdict(oracle_mod.check_linearizable(h2, m, 3)) == base
+
+
+def test_prefix_closure(oracle_mod):
+    # a linearizable history stays linearizable when truncated (open invokes become crashed ops)
+    spec = synth.SynthSpec("bank", n_ops=150, n_clients=4, seed=3)
+    h = synth.generate(spec)
+    m = MODELS["bank"]()
+    assert oracle_mod.check_linearizable(h, m, 3)["valid"] == H.VALID
+    for cut in (17, 60, 111, 250):
+        hp = h.shard(0)
+        sl = slice(0, cut)
+        hp2 = H.FlatHistory(hp.type[sl].copy(), hp.f[sl].copy(), hp.flags[sl].copy(), hp.process[sl].copy(),
+                            hp.index[sl].copy(), hp.time_ns[sl].copy(), hp.a[sl].copy(), hp.b[sl].copy(),
+                            hp.c[sl].copy(), hp.payload_off[sl].copy(), hp.payload_len[sl].copy(), hp.payload,
+                            np.array([0, cut], np.int64), hp.key_ids)
+        assert oracle_mod.check_linearizable(hp2, m, 3)["valid"] == H.VALID
