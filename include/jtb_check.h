@@ -216,6 +216,11 @@ int jtb_check_set_full(jtb_ctx* ctx, const jtb_history* h, int linearizable, jtb
 int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* accounts,
                           int64_t total_amount, jtb_bank_result* out);
 
+/* ---- diagnostics: counters of the last jtb_check_linearizable call ------------------------------ *
+ * out[0..11] = configs, probes, expansions, ring tail, ring head, idle polls, max probe length,
+ * table slots, grid CTAs, ring entries, kernel launches (pause/resume growth + 1), kernel microseconds */
+int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n);
+
 /* ---- K2 in isolation: visited-table probe/insert microbenchmark (roofline evidence) ----------- *
  * Inserts n_keys pseudo-random 128-bit keys then probes them `rounds` times; returns device
  * seconds for insert and probe phases.  variant selects the probe path.          */

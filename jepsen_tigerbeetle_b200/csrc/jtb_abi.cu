@@ -32,6 +32,7 @@ struct jtb_ctx {
     // pinned staging
     void* pin = nullptr;
     size_t pin_cap = 0;
+    unsigned long long stats[16] = {0};
 };
 
 namespace {
@@ -68,20 +69,20 @@ int upload(jtb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
 }
 
 template <int MODEL, int KW>
-int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int32_t init_reg, int grid, size_t smem) {
+int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem) {
     auto k = wgl_search_kernel<MODEL, KW>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WGL_THREADS, smem, ctx->stream>>>(p, neg_ok, init_reg);
+    k<<<grid, WGL_THREADS, smem, ctx->stream>>>(p, neg_ok);
     CK(cudaGetLastError());
     return 0;
 }
 
 template <int MODEL>
-int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int32_t init_reg, int grid, size_t smem) {
+int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid, size_t smem) {
     switch (kw) {
-    case 2: return launch_wgl<MODEL, 2>(ctx, p, neg_ok, init_reg, grid, smem);
-    case 4: return launch_wgl<MODEL, 4>(ctx, p, neg_ok, init_reg, grid, smem);
-    case 8: return launch_wgl<MODEL, 8>(ctx, p, neg_ok, init_reg, grid, smem);
+    case 2: return launch_wgl<MODEL, 2>(ctx, p, neg_ok, grid, smem);
+    case 4: return launch_wgl<MODEL, 4>(ctx, p, neg_ok, grid, smem);
+    case 8: return launch_wgl<MODEL, 8>(ctx, p, neg_ok, grid, smem);
     }
     ctx->err = "unsupported key width";
     return -1;
@@ -185,49 +186,59 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     }
     double kernel_s = 0;
     uint64_t configs = 0, probes = 0;
+    ctx->stats[10] = 0;
+    Ctrl hc;
+    std::memset(&hc, 0, sizeof hc);
+    std::vector<int> h_found(n_shards, 0), h_max(n_shards, 0);
     if (!searchable.empty()) {
         if (upload(ctx, ctx->rows, P.rows) || upload(ctx, ctx->ops, P.ops) || upload(ctx, ctx->read_bal, P.read_bal) ||
             upload(ctx, ctx->classes, P.classes) || upload(ctx, ctx->cls_inv, P.cls_inv_pos))
             return -1;
-        // work pool
-        const size_t pool_bytes = 1ull << 30;
-        if (ensure(ctx, ctx->pool, pool_bytes)) return -1;
-        const uint64_t pool_cap = pool_bytes / (EW * 8);
-        if (init_entries.size() / EW > pool_cap) { ctx->err = "too many shards for the work pool"; return -1; }
         if (ensure(ctx, ctx->ctrl, sizeof(Ctrl)) || ensure(ctx, ctx->found, n_shards * sizeof(int)) ||
             ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
             return -1;
-        // deque sizing
+        // CTA deque / grid
         const int cand_rounds = P.S_pad / 32, cls_rounds = (P.max_nc + 31) / 32;
         const uint32_t worst_push = WGL_WARPS * 32 * (cand_rounds + cls_rounds);
         uint32_t deque_cap = 512;
         while (deque_cap < 2 * worst_push) deque_cap <<= 1;
+        const uint32_t stage_cap = deque_cap;
         const size_t smem = (size_t)deque_cap * EW * 8;
         if (smem > 200 * 1024) { ctx->err = "too many crashed-op classes for the shared-memory deque"; return -1; }
         int ctas_per_sm = (int)std::min<size_t>(4, (220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, ctas_per_sm);
-        int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;
-        // table sizing with escalation on TABLE_FULL
+        const int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;
+        const uint64_t per_step_push = (uint64_t)grid * stage_cap;  // worst case children of one step of every CTA
+        // work ring
+        uint64_t ring_entries = 1ull << 22;
+        while (ring_entries < 4 * per_step_push + 2 * searchable.size()) ring_entries <<= 1;
+        if (ensure(ctx, ctx->pool, ring_entries * EW * 8)) return -1;
+        CK(cudaMemsetAsync(ctx->pool.p, 0, ring_entries * EW * 8, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->pool.p, init_entries.data(), init_entries.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        // visited table: start at 1 GiB (or the caller's size), grow x4 on load > 0.7 without losing work
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t reserve = (size_t)4 << 30;
         size_t max_table = ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)64 << 30;
-        max_table = std::min(max_table, ctx->table.cap + (free_b > ((size_t)2 << 30) ? free_b - ((size_t)2 << 30) : 0));
-        size_t table_bytes = std::min<size_t>(max_table, ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)256 << 20);
-        std::vector<int> h_found(n_shards), h_max(n_shards);
-        Ctrl hc;
+        max_table = std::min(max_table, ctx->table.cap + (free_b > reserve ? free_b - reserve : 0));
+        size_t table_bytes = std::min<size_t>(max_table, ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)1 << 30);
+        uint64_t n_slots = 1;
+        while (n_slots * 2 * KW * 8 <= table_bytes) n_slots <<= 1;
+        if (ensure(ctx, ctx->table, n_slots * KW * 8)) return -1;
+        CK(cudaMemsetAsync(ctx->table.p, 0, n_slots * KW * 8, ctx->stream));
+        hc.tail = searchable.size();
+        hc.created = searchable.size();
+        hc.n_undecided = (int)searchable.size();
+        CK(cudaMemcpyAsync(ctx->ctrl.p, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));
+        for (int s = 0; s < n_shards; ++s) h_max[s] = (int)P.rank_base[s];
+        CK(cudaMemcpyAsync(ctx->maxrank.p, h_max.data(), n_shards * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        DevBuf ring2, table2;  // growth targets (freed below)
+        auto free_tmp = [&]() { if (ring2.p) cudaFree(ring2.p); if (table2.p) cudaFree(table2.p); ring2 = DevBuf(); table2 = DevBuf(); };
+        int attempts = 0;
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
         for (;;) {
-            uint64_t n_slots = 1;
-            while (n_slots * 2 * KW * 8 <= table_bytes) n_slots <<= 1;
-            if (ensure(ctx, ctx->table, n_slots * KW * 8)) return -1;
-            CK(cudaMemsetAsync(ctx->table.p, 0, n_slots * KW * 8, ctx->stream));
-            std::memset(&hc, 0, sizeof hc);
-            hc.pool_top = searchable.size();
-            hc.n_undecided = (int)searchable.size();
-            CK(cudaMemcpyAsync(ctx->ctrl.p, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));
-            for (int s = 0; s < n_shards; ++s) h_max[s] = (int)P.rank_base[s];
-            CK(cudaMemcpyAsync(ctx->maxrank.p, h_max.data(), n_shards * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->pool.p, init_entries.data(), init_entries.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ++attempts;
             WglParams p{};
             p.rows = (const int32_t*)ctx->rows.p;
             p.ops = (const int4*)ctx->ops.p;
@@ -236,8 +247,9 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.cls_inv_pos = (const int32_t*)ctx->cls_inv.p;
             p.table = (uint64_t*)ctx->table.p;
             p.slot_mask = n_slots - 1;
-            p.pool = (uint64_t*)ctx->pool.p;
-            p.pool_cap = pool_cap;
+            p.ring = (uint64_t*)ctx->pool.p;
+            p.ring_mask = ring_entries - 1;
+            p.ring_guard = ring_entries - 3 * per_step_push;
             p.ctrl = (Ctrl*)ctx->ctrl.p;
             p.shard_found = (int*)ctx->found.p;
             p.shard_max_rank = (int*)ctx->maxrank.p;
@@ -254,27 +266,63 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             }
             p.time_budget_ns = (unsigned long long)ctx->opts.time_budget_ms * 1000000ull;
             p.deque_cap = deque_cap;
-            CK(cudaEventRecord(ctx->ev0, ctx->stream));
             int rc;
-            if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, 0, grid, smem);
-            else rc = launch_wgl_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, m->init_value, grid, smem);
-            if (rc) return rc;
-            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem);
+            else rc = launch_wgl_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, grid, smem);
+            if (rc) { free_tmp(); return rc; }
             CK(cudaMemcpyAsync(&hc, ctx->ctrl.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(h_found.data(), ctx->found.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(h_max.data(), ctx->maxrank.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            float ms = 0;
-            CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-            kernel_s += ms * 1e-3;
-            configs += hc.configs;
-            probes += hc.probes;
-            if (hc.stop == 2 && hc.cause == JTB_CAUSE_TABLE_FULL && table_bytes < max_table) {
-                table_bytes = std::min(max_table, table_bytes * 16);  // escalate and restart
-                continue;
+            const bool grow_table = hc.stop == 2 && hc.cause == JTB_CAUSE_TABLE_FULL && n_slots * KW * 8 * 4 <= max_table;
+            const bool grow_ring = hc.stop == 2 && hc.cause == CAUSE_RING_FULL && ring_entries * EW * 8 * 4 <= ((size_t)16 << 30);
+            if (!grow_table && !grow_ring) break;
+            // ---- pause/resume: the live work is exactly the non-zero ring slots ---------------------
+            const uint64_t new_ring_entries = grow_ring ? ring_entries * 4 : ring_entries;
+            if (ensure(ctx, ring2, new_ring_entries * EW * 8)) { free_tmp(); return -1; }
+            CK(cudaMemsetAsync(ring2.p, 0, new_ring_entries * EW * 8, ctx->stream));
+            Ctrl* dc = (Ctrl*)ctx->ctrl.p;
+            CK(cudaMemsetAsync(&dc->tail, 0, sizeof(unsigned long long), ctx->stream));
+            if (EW == 2) ring_compact_kernel<2><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->pool.p, ring_entries - 1, 0, ring_entries, (uint64_t*)ring2.p, new_ring_entries - 1, &dc->tail);
+            else if (EW == 4) ring_compact_kernel<4><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->pool.p, ring_entries - 1, 0, ring_entries, (uint64_t*)ring2.p, new_ring_entries - 1, &dc->tail);
+            else if (EW == 6) ring_compact_kernel<6><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->pool.p, ring_entries - 1, 0, ring_entries, (uint64_t*)ring2.p, new_ring_entries - 1, &dc->tail);
+            else if (EW == 8) ring_compact_kernel<8><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->pool.p, ring_entries - 1, 0, ring_entries, (uint64_t*)ring2.p, new_ring_entries - 1, &dc->tail);
+            else ring_compact_kernel<12><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->pool.p, ring_entries - 1, 0, ring_entries, (uint64_t*)ring2.p, new_ring_entries - 1, &dc->tail);
+            CK(cudaGetLastError());
+            std::swap(ctx->pool, ring2);
+            ring_entries = new_ring_entries;
+            CK(cudaMemsetAsync(&dc->head, 0, sizeof(unsigned long long), ctx->stream));
+            CK(cudaMemsetAsync(&dc->stop, 0, 2 * sizeof(int), ctx->stream));  // stop, cause
+            if (grow_table) {
+                const uint64_t new_slots = n_slots * 4;
+                if (ensure(ctx, table2, new_slots * KW * 8)) { free_tmp(); return -1; }
+                CK(cudaMemsetAsync(table2.p, 0, new_slots * KW * 8, ctx->stream));
+                if (KW == 2) table_rehash_kernel<2><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
+                else if (KW == 4) table_rehash_kernel<4><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
+                else table_rehash_kernel<8><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(ctx->stream));
+                std::swap(ctx->table, table2);
+                if (table2.p) { cudaFree(table2.p); table2 = DevBuf(); }  // release the old table right away
+                n_slots = new_slots;
             }
-            break;
         }
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaMemcpyAsync(h_found.data(), ctx->found.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_max.data(), ctx->maxrank.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_tmp();
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        kernel_s = ms * 1e-3;
+        configs = hc.configs;
+        probes = hc.probes;
+        {
+            unsigned long long* st = ctx->stats;
+            st[0] = hc.configs; st[1] = hc.probes; st[2] = hc.expansions; st[3] = hc.tail;
+            st[4] = hc.head; st[5] = hc.polls; st[6] = hc.max_probe_len; st[7] = n_slots;
+            st[8] = (unsigned long long)grid; st[9] = ring_entries; st[10] = (unsigned long long)attempts;
+            st[11] = (unsigned long long)(ms * 1e3);
+        }
+        if (hc.stop == 2 && hc.cause == CAUSE_RING_FULL) hc.cause = JTB_CAUSE_BUDGET;
         for (int s : searchable) {
             jtb_lin_shard& r = shards[s];
             if (h_found[s]) {
@@ -320,6 +368,12 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
     return run_bank_totals(ctx->stream, ctx->ev0, ctx->ev1, h, accounts, total_amount, out, ctx->err);
+}
+
+int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n) {
+    if (!ctx) return -1;
+    for (int i = 0; i < n && i < 16; ++i) out[i] = ctx->stats[i];
+    return 0;
 }
 
 int jtb_table_bench(jtb_ctx* ctx, uint64_t n_keys, int variant, int rounds, double* insert_seconds,

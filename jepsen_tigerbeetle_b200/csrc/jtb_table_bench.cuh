@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(256) tb_probe_buckets_ldg(const uint64_t* tabl
             for (int tries = 0; tries < 64; ++tries) {
                 const bool hit = live[u] && cur[u].lo == k[u][0] && cur[u].hi == k[u][1];
                 const bool empty = live[u] && cur[u].lo == 0 && cur[u].hi == 0;
-                const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);
-                const unsigned hits = __ballot_sync(0xffffffffu, hit) & gm;
-                const unsigned empties = __ballot_sync(0xffffffffu, empty) & gm;
+                const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);  // the 8 lanes sharing this key
+                const unsigned hits = __ballot_sync(gm, hit);
+                const unsigned empties = __ballot_sync(gm, empty);
                 if (hits) { if (sub == 0) mine++; break; }
                 if (empties || !live[u]) break;
                 b[u] = (b[u] + 1) & bucket_mask;

@@ -13,10 +13,19 @@
 //    (model step inlined), the lane that linearizes the frontier op advances the frontier with
 //    ballot/match arithmetic, every consistent child is probed/inserted in the global visited table
 //    (16 B slots, ld.global.cg.v2.u64 probe + atom.cas.b128 insert), new children are pushed on the
-//    CTA's shared-memory deque.  Depth-first order (LIFO) keeps the frontier deep.
-//  * Work distribution: CTA-local deque in shared memory shared by its warps; oldest entries are
-//    donated to a global LIFO pool when the deque is full or other CTAs are hungry; idle CTAs refill
-//    from the pool.  Termination: no busy CTA and an empty pool (checked under the pool lock).
+//    CTA's shared-memory staging buffer.
+//  * Work distribution: depth-first locally, breadth-first globally, no locks.
+//      - each CTA keeps a LIFO deque in shared memory shared by its 8 warps (deep dives find the
+//        linearization of a valid history quickly);
+//      - an idle warp takes a read TICKET (ring position from atomicAdd(head)) on a global FIFO ring in HBM
+//        and polls that slot; head - tail > 0 is therefore the number of hungry warps;
+//      - a CTA whose deque is nearly full, or that sees hungry warps, donates its OLDEST entries with one
+//        atomicAdd(tail) (payload words first, word0 = ready flag last); the ticket holder zeroes the slot.
+//    A lock-based LIFO pool with stealing was measured first and starved (46 M idle spins for 4.8 M
+//    configs); a pure FIFO was 50x faster on exhaustive searches but explodes on valid histories with
+//    crashed ops (breadth-first visits the whole reachable space).  This hybrid keeps both properties.
+//    Termination: expanded == created.  Pause/resume: on pause every CTA flushes its deque, so the live
+//    work is exactly the non-zero ring slots and the host can grow the table or the ring and relaunch.
 //  * Verdict: first config whose frontier passes the shard's last return => VALID (early exit);
 //    exhaustion => INVALID with witness = furthest frontier rank reached (atomicMax), which is the
 //    earliest :ok completion whose history prefix is not linearizable.
@@ -33,18 +42,19 @@ struct __align__(16) K128 {
 };
 
 struct Ctrl {
-    // hot, read every step by one thread per CTA
-    int stop;            // 0 run, 1 finished (all shards decided or exhausted), 2 aborted (cause)
-    int n_hungry;        // CTAs with an empty deque
-    int cause;           // JTB_CAUSE_* when stop == 2
-    int n_busy;          // CTAs holding work
-    int pool_lock;
-    int n_undecided;     // shards not yet found VALID
-    unsigned long long pool_top;   // entries in the global pool
-    unsigned long long t0;         // %globaltimer at first CTA start
-    // statistics (flushed at CTA exit)
-    unsigned long long configs, probes, expansions, pool_pushes, pool_pops, idle_spins, max_probe_len;
+    // each hot word on its own 128 B line (same-line atomics serialise in one L2 slice)
+    alignas(128) int stop;         // 0 run, 1 finished (all shards decided or exhausted), 2 paused/aborted (cause)
+    int cause;                     // JTB_CAUSE_* / CAUSE_RING_FULL when stop == 2
+    int n_undecided;               // shards not yet found VALID
+    alignas(128) unsigned long long head;   // read tickets handed to warps (ring positions)
+    alignas(128) unsigned long long tail;   // entries pushed (ring positions reserved for writing)
+    alignas(128) unsigned long long created;   // configs created (initial + every new child)
+    alignas(128) unsigned long long expanded;  // configs expanded; created == expanded <=> search exhausted
+    alignas(128) unsigned long long configs;  // distinct configs inserted (amortised tally; budget / load guard)
+    alignas(128) unsigned long long t0;       // %globaltimer at first CTA start
+    unsigned long long probes, expansions, polls, max_probe_len, max_live;
 };
+constexpr int CAUSE_RING_FULL = 100;  // internal: the host grows the ring and resumes
 
 struct WglParams {
     const int32_t* rows;
@@ -54,8 +64,9 @@ struct WglParams {
     const int32_t* cls_inv_pos;
     uint64_t* table;        // slots of KW 64-bit words
     uint64_t slot_mask;     // n_slots - 1
-    uint64_t* pool;         // entries of EW words
-    uint64_t pool_cap;      // entries
+    uint64_t* ring;         // work queue: entries of EW words, word0 != 0 <=> slot holds an entry
+    uint64_t ring_mask;     // ring entries - 1
+    uint64_t ring_guard;    // pause when (tail - head) exceeds this
     Ctrl* ctrl;
     int* shard_found;       // [n_shards]
     int* shard_max_rank;    // [n_shards] furthest frontier reached (global rank)
@@ -63,7 +74,7 @@ struct WglParams {
     unsigned long long max_configs;   // stop (UNKNOWN) once this many configs were inserted
     int budget_cause;                 // JTB_CAUSE_BUDGET or JTB_CAUSE_TABLE_FULL (load guard)
     unsigned long long time_budget_ns;
-    uint32_t deque_cap;     // power of two
+    uint32_t deque_cap;     // entries in the CTA's shared-memory deque (power of two)
 };
 
 constexpr uint64_t KEY_VALID = 1ull << 63;
@@ -213,180 +224,154 @@ __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t 
 template <int MODEL, int KW>
 struct EntryLayout {
     static constexpr bool HAS_BAL = MODEL == JTB_MODEL_BANK;
-    static constexpr int EW = KW + (HAS_BAL ? 4 : 0);  // 64-bit words per deque/pool entry
+    static constexpr int EW = KW + (HAS_BAL ? 4 : 0);  // 64-bit words per ring entry
 };
 
 constexpr int WGL_WARPS = 8;
 constexpr int WGL_THREADS = WGL_WARPS * 32;
+constexpr unsigned WGL_MAX_DONATE = 64;       // per step, when donating to hungry warps
 
 struct CtaShared {
-    uint32_t top, bot;         // deque indices (monotonic, masked on use)
-    uint32_t top_snap;
-    int stop, hungry, idle;
-    uint32_t xfer_n;
-    unsigned long long xfer_off;
-    unsigned long long wit_cache;  // (shard << 32 | furthest rank): filter for the witness atomicMax
-    unsigned long long configs, probes, expansions, pool_pushes, pool_pops, idle_spins;
-    int max_probe_len;
+    int stop;
+    unsigned top, bot;              // local LIFO deque (monotonic indices, masked on use)
+    unsigned pop_top, don_bot;      // snapshots for this step's readers
+    unsigned n_local, n_don;
+    unsigned local_mask;            // warps that pop a local entry this step
+    unsigned ticket_mask;           // warps that currently hold a ring ticket
+    unsigned assign_mask;           // warps that receive a new ticket this step
+    unsigned n_exp, n_new;          // expansions / new children of the running step
+    unsigned backoff;
+    unsigned long long ticket_base, don_base;
+    unsigned long long wit_cache;   // (shard << 32 | furthest rank): filter for the witness atomicMax
+    unsigned long long polls;
     int since_flush;
 };
 
-__device__ __forceinline__ void pool_lock(Ctrl* c) {
-    while (atomicCAS(&c->pool_lock, 0, 1) != 0) __nanosleep(100);
-    __threadfence();
-}
-__device__ __forceinline__ void pool_unlock(Ctrl* c) {
-    __threadfence();
-    atomicExch(&c->pool_lock, 0);
-}
+__device__ __forceinline__ uint64_t ld_volatile64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 
 template <int MODEL, int KW>
-__global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglParams p, const int neg_ok,
-                                                                    const int32_t init_reg) {
+__global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglParams p, const int neg_ok) {
     using L = EntryLayout<MODEL, KW>;
     constexpr int EW = L::EW;
     extern __shared__ __align__(16) uint64_t s_deque[];  // deque_cap * EW words
     __shared__ CtaShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t cap_mask = p.deque_cap - 1;
     Ctrl* ctrl = p.ctrl;
     const int cand_rounds = p.S_pad / 32;
     const int cls_rounds = (p.max_nc + 31) / 32;
-    const uint32_t worst_push = WGL_WARPS * 32 * (cand_rounds + cls_rounds);
-    const uint32_t high = p.deque_cap - worst_push;
+    const unsigned cap_mask = p.deque_cap - 1;
+    const unsigned worst_push = WGL_WARPS * 32 * (cand_rounds + cls_rounds);
+    const unsigned high = p.deque_cap - worst_push;
 
     if (tid == 0) {
-        sh.top = sh.bot = 0;
-        sh.stop = 0; sh.hungry = 0; sh.idle = 1;  // starts idle: not counted in n_busy
+        sh.stop = 0; sh.top = sh.bot = 0;
+        sh.ticket_mask = 0; sh.n_exp = 0; sh.n_new = 0;
+        sh.backoff = 32;
         sh.wit_cache = ~0ull;
-        sh.configs = sh.probes = sh.expansions = sh.pool_pushes = sh.pool_pops = sh.idle_spins = 0;
-        sh.max_probe_len = 0; sh.since_flush = 0;
-        atomicAdd(&ctrl->n_hungry, 1);
-        unsigned long long now = globaltimer();
+        sh.polls = 0; sh.since_flush = 0;
+        const unsigned long long now = globaltimer();
         atomicCAS(&ctrl->t0, 0ull, now);
     }
-    unsigned long long my_configs = 0, my_probes = 0;
-    int my_steps = 0;
-    int my_max_probe = 0;
+    bool has_ticket = false;
+    unsigned long long ticket = 0;
+    unsigned long long my_configs = 0, my_probes = 0, my_expansions = 0;
+    int my_steps = 0, my_max_probe = 0;
+    bool exiting = false;
 
     for (;;) {
-        __syncthreads();  // (1) pushes of the previous step are complete
+        __syncthreads();  // (A) pushes of the previous step are complete
         if (tid == 0) {
-            sh.stop = ld_volatile(&ctrl->stop);
-            sh.hungry = ld_volatile(&ctrl->n_hungry);
-            sh.top_snap = sh.top;
-            if (++sh.since_flush >= 64) {  // budget checks, amortised
-                sh.since_flush = 0;
-                if (p.time_budget_ns && globaltimer() - ld_volatile(&ctrl->t0) > p.time_budget_ns) {
-                    atomicCAS(&ctrl->cause, 0, JTB_CAUSE_BUDGET);
-                    atomicExch(&ctrl->stop, 2);
+            // ---- account the previous step: created before expanded (termination invariant) --------
+            if (sh.n_new) { atomicAdd(&ctrl->created, (unsigned long long)sh.n_new); __threadfence(); }
+            if (sh.n_exp) atomicAdd(&ctrl->expanded, (unsigned long long)sh.n_exp);
+            const bool was_idle = sh.n_exp == 0;
+            sh.n_exp = 0; sh.n_new = 0;
+            int stop = ld_volatile(&ctrl->stop);
+            const unsigned long long h = ld_volatile(&ctrl->head);
+            const unsigned long long t = ld_volatile(&ctrl->tail);
+            const unsigned size = sh.top - sh.bot;
+            if (stop == 0) {
+                if (t > h && t - h > p.ring_guard) {  // ring nearly full: pause (flush happens next step)
+                    atomicCAS(&ctrl->cause, 0, CAUSE_RING_FULL);
+                    atomicCAS(&ctrl->stop, 0, 2);
                 }
-            }
-        }
-        __syncthreads();  // (2)
-        if (sh.stop) break;
-        uint32_t top = sh.top_snap;
-        uint32_t size = top - sh.bot;
-
-        if (size == 0) {
-            // ---------------- acquire from the global pool (or detect termination) -------------
-            if (tid == 0) {
-                sh.xfer_n = 0;
-                if (!sh.idle) {
-                    sh.idle = 1;
-                    atomicAdd(&ctrl->n_hungry, 1);
-                    atomicSub(&ctrl->n_busy, 1);
-                }
-                unsigned long long pt = ld_volatile(&ctrl->pool_top);
-                if (pt > 0) {
-                    pool_lock(ctrl);
-                    pt = ld_volatile(&ctrl->pool_top);
-                    if (pt > 0) {
-                        int hungry = max(1, ld_volatile(&ctrl->n_hungry));
-                        unsigned long long take = pt / (unsigned)hungry;
-                        take = take < 1 ? 1 : take > 4 * WGL_WARPS ? 4 * WGL_WARPS : take;
-                        sh.xfer_n = (uint32_t)take;
-                        sh.xfer_off = pt - take;
-                        *(volatile unsigned long long*)&ctrl->pool_top = pt - take;
-                        atomicAdd(&ctrl->n_busy, 1);
-                        atomicSub(&ctrl->n_hungry, 1);
-                        sh.idle = 0;
-                        sh.pool_pops++;
-                        // lock stays held until the entries are copied out
-                    } else {
-                        pool_unlock(ctrl);
+                if (++sh.since_flush >= 64) {
+                    sh.since_flush = 0;
+                    if (p.time_budget_ns && globaltimer() - ld_volatile(&ctrl->t0) > p.time_budget_ns) {
+                        atomicCAS(&ctrl->cause, 0, JTB_CAUSE_BUDGET);
+                        atomicCAS(&ctrl->stop, 0, 2);
                     }
-                } else if (ld_volatile(&ctrl->n_busy) == 0) {
-                    pool_lock(ctrl);
-                    if (ld_volatile(&ctrl->pool_top) == 0 && ld_volatile(&ctrl->n_busy) == 0)
-                        atomicCAS(&ctrl->stop, 0, 1);  // search space exhausted
-                    pool_unlock(ctrl);
+                }
+                if (was_idle && size == 0) {
+                    // nothing local, nothing served: termination test (expanded first, then created)
+                    const unsigned long long ex = ld_volatile(&ctrl->expanded);
+                    const unsigned long long cr = ld_volatile(&ctrl->created);
+                    if (ex == cr) { atomicCAS(&ctrl->stop, 0, 1); stop = ld_volatile(&ctrl->stop); }
+                    else {
+                        __nanosleep(sh.backoff);
+                        if (sh.backoff < 1024) sh.backoff <<= 1;
+                    }
                 } else {
-                    sh.idle_spins++;
-                    __nanosleep(500);
+                    sh.backoff = 32;
                 }
             }
-            __syncthreads();
-            const uint32_t n = sh.xfer_n;
-            if (n) {
-                const uint64_t* src = p.pool + sh.xfer_off * EW;
-                for (uint32_t i = tid; i < n * EW; i += WGL_THREADS) {
-                    const uint32_t e = i / EW, w = i % EW;
-                    s_deque[((top + e) & cap_mask) * EW + w] = ldcg64(src + i);
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    pool_unlock(ctrl);
-                    sh.top = top + n;
-                }
+            sh.stop = stop;
+            // ---- donation: deque nearly full, other warps hungry (tickets waiting), or pausing ---------
+            const unsigned long long hunger = h > t ? h - t : 0;
+            const unsigned free_warps = ~sh.ticket_mask & ((1u << WGL_WARPS) - 1);
+            const unsigned keep = max(1, __popc(free_warps));  // what this CTA can pop next step
+            unsigned n_don = 0;
+            if (stop == 2) n_don = size;  // pause: all live work must be in the ring
+            else if (size > high) n_don = size - p.deque_cap / 4;
+            else if (hunger && size > keep)
+                n_don = (unsigned)min((unsigned long long)min(size - keep, WGL_MAX_DONATE), hunger);
+            sh.n_don = n_don;
+            sh.don_bot = sh.bot;
+            if (n_don) {
+                sh.don_base = atomicAdd(&ctrl->tail, (unsigned long long)n_don);
+                sh.bot += n_don;
             }
-            continue;
+            // ---- local pops go to warps that hold no ticket; the remaining ticketless warps take one ----
+            unsigned n_local = stop ? 0 : min(size - n_don, (unsigned)__popc(free_warps));
+            unsigned local_mask = 0, rest = free_warps;
+            for (unsigned k = 0; k < n_local; ++k) { const unsigned b = rest & (0u - rest); local_mask |= b; rest ^= b; }
+            sh.local_mask = local_mask;
+            sh.n_local = n_local;
+            sh.pop_top = sh.top;
+            sh.top -= n_local;
+            const unsigned need = stop ? 0 : rest;
+            sh.assign_mask = need;
+            if (need) {
+                sh.ticket_base = atomicAdd(&ctrl->head, (unsigned long long)__popc(need));
+                sh.ticket_mask |= need;
+            }
         }
-
-        if (size > high || (sh.hungry > 0 && size >= 2 * WGL_WARPS)) {
-            // ---------------- donate the oldest entries to the global pool ----------------------
-            const uint32_t n = size > high ? size - p.deque_cap / 4 : min(size / 2, 4u * WGL_WARPS * 4u);
-            if (tid == 0) {
-                pool_lock(ctrl);
-                unsigned long long pt = ld_volatile(&ctrl->pool_top);
-                sh.xfer_off = pt;
-                sh.xfer_n = n;
-                if (pt + n > p.pool_cap) {
-                    sh.xfer_n = 0;
-                    atomicCAS(&ctrl->cause, 0, JTB_CAUSE_BUDGET);
-                    atomicExch(&ctrl->stop, 2);
-                    pool_unlock(ctrl);
-                }
-            }
-            __syncthreads();
-            if (sh.xfer_n) {
-                uint64_t* dst = p.pool + sh.xfer_off * EW;
-                const uint32_t bot = sh.bot;
-                for (uint32_t i = tid; i < n * EW; i += WGL_THREADS) {
-                    const uint32_t e = i / EW, w = i % EW;
-                    dst[i] = s_deque[((bot + e) & cap_mask) * EW + w];
-                }
+        __syncthreads();  // (B)
+        if (sh.stop == 1) break;
+        exiting = sh.stop == 2;
+        // ---- donation copy: oldest local entries -> ring (payload first, word0 = ready flag last) -----
+        {
+            const unsigned n_don = sh.n_don;
+            for (unsigned i = tid; i < n_don; i += WGL_THREADS) {
+                uint64_t* dst = p.ring + ((sh.don_base + i) & p.ring_mask) * EW;
+                const uint64_t* src = &s_deque[(size_t)((sh.don_bot + i) & cap_mask) * EW];
+#pragma unroll
+                for (int k = 1; k < EW; ++k) dst[k] = src[k];
                 __threadfence();
-                __syncthreads();
-                if (tid == 0) {
-                    *(volatile unsigned long long*)&ctrl->pool_top = sh.xfer_off + n;
-                    pool_unlock(ctrl);
-                    sh.bot = bot + n;
-                    sh.pool_pushes++;
-                }
-                size -= n;
+                *(volatile uint64_t*)dst = src[0];
             }
-            __syncthreads();
-            if (sh.xfer_n == 0) continue;  // aborted
         }
-
-        // ---------------- pop: the top min(size, warps) entries, one per warp ----------------------
-        const uint32_t take = min(size, (uint32_t)WGL_WARPS);
+        // ---- fetch: a local entry, or poll my ring ticket ----------------------------------------------
         uint64_t w[KW];
         int32_t pbal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const bool active = warp < (int)take;
-        if (active) {
-            const uint64_t* e = &s_deque[((top - 1 - warp) & cap_mask) * EW];
+        bool ready = false;
+        if ((sh.assign_mask >> warp) & 1u) {
+            ticket = sh.ticket_base + __popc(sh.assign_mask & ((1u << warp) - 1));
+            has_ticket = true;
+        }
+        if ((sh.local_mask >> warp) & 1u) {
+            const unsigned k = __popc(sh.local_mask & ((1u << warp) - 1));
+            const uint64_t* e = &s_deque[(size_t)((sh.pop_top - 1 - k) & cap_mask) * EW];
 #pragma unroll
             for (int i = 0; i < KW; ++i) w[i] = e[i];
             if constexpr (L::HAS_BAL) {
@@ -397,179 +382,206 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                     pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
                 }
             }
-        }
-        if (tid == 0) sh.top = top - take;
-        __syncthreads();  // (3) popped entries are in registers; pushes may now reuse the space
-        if (!active) continue;
-
-        // ---------------- expand (warp-synchronous) -------------------------------------------------
-        const int gj = (int)((w[0] >> 32) & 0x3fffffffu);
-        const int32_t preg = (int32_t)(uint32_t)w[0];
-        const int32_t* row = p.rows + (size_t)gj * p.row_words;
-        const int32_t extra = __ldg(row + p.S_pad + (lane & 15));
-        const int fr_pos = __shfl_sync(0xffffffffu, extra, 8);
-        const int shard = __shfl_sync(0xffffffffu, extra, 9);
-        const int gj_end = __shfl_sync(0xffffffffu, extra, 10);
-        const int cls_base = __shfl_sync(0xffffffffu, extra, 11);
-        const int ncls = __shfl_sync(0xffffffffu, extra, 12);
-        const int rslot = __shfl_sync(0xffffffffu, extra, 13);
-        if (p.n_shards > 1 && ld_volatile(&p.shard_found[shard])) continue;  // shard already VALID
-        int n_new_total = 0, n_probe_total = 0;
-
-        auto push_children = [&](bool is_new, const uint64_t (&cw)[KW], const int32_t (&cbal)[8]) {
-            const unsigned newm = __ballot_sync(0xffffffffu, is_new);
-            if (newm == 0) return;
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&sh.top, (uint32_t)__popc(newm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (is_new) {
-                uint64_t* e = &s_deque[((base + __popc(newm & ((1u << lane) - 1))) & cap_mask) * EW];
+            ready = true;
+        } else if (has_ticket && !exiting) {
+            uint64_t* slot = p.ring + (ticket & p.ring_mask) * EW;
+            w[0] = ld_volatile64(slot);
+            ready = w[0] != 0;   // warp-uniform: all lanes load the same address
+            if (ready) {
+                __threadfence();  // acquire: payload words were written before word0
 #pragma unroll
-                for (int i = 0; i < KW; ++i) e[i] = cw[i];
+                for (int i = 1; i < KW; ++i) w[i] = ldcg64(slot + i);
                 if constexpr (L::HAS_BAL) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        e[KW + i] = (uint64_t)(uint32_t)cbal[2 * i] | ((uint64_t)(uint32_t)cbal[2 * i + 1] << 32);
-                }
-            }
-            n_new_total += __popc(newm);
-        };
-
-        // -- candidates: ops in the open slots
-        for (int r = 0; r < cand_rounds; ++r) {
-            const int t = r * 32 + lane;
-            const int opid = __ldg(row + t);
-            bool cand = opid >= 0 && !((w[1] >> t) & 1ull);
-            int4 op = make_int4(OP_IMPOSSIBLE, 0, 0, 0);
-            if (cand) op = __ldg(p.ops + opid);
-            int32_t creg = preg;
-            int32_t cbal[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-            bool ok = cand && model_step<MODEL>(op, creg, cbal, p.read_bal, neg_ok != 0);
-            const bool is_front = t == rslot;
-            uint64_t cw[KW];
-#pragma unroll
-            for (int i = 0; i < KW; ++i) cw[i] = w[i];
-            int cgj = gj;
-            // frontier advance, warp-cooperative, for the child that linearizes the frontier op
-            const unsigned front_ok = __ballot_sync(0xffffffffu, ok && is_front);
-            if (front_ok) {
-                uint64_t m = w[1];
-                int adv = 0;
-                const int32_t* rw = row;
-                int32_t ex = extra;
-                for (;;) {
-                    const int32_t word = __shfl_sync(0xffffffffu, ex, lane >> 2);
-                    const int sl = (word >> (8 * (lane & 3))) & 0xff;
-                    const bool setb = sl != 0xff && ((m >> sl) & 1ull);
-                    const unsigned peers = __match_any_sync(0xffffffffu, sl);
-                    const bool pass = setb && (peers & ((1u << lane) - 1)) == 0;
-                    const unsigned pm = __ballot_sync(0xffffffffu, pass);
-                    const int n = pm == 0xffffffffu ? 32 : __ffs(~pm) - 1;
-                    const uint64_t clr = (lane < n) ? (1ull << sl) : 0ull;
-                    const uint32_t clo = __reduce_or_sync(0xffffffffu, (uint32_t)clr);
-                    const uint32_t chi = __reduce_or_sync(0xffffffffu, (uint32_t)(clr >> 32));
-                    m &= ~((uint64_t)clo | ((uint64_t)chi << 32));
-                    adv += n;
-                    if (n < 32) break;
-                    rw += (size_t)32 * p.row_words;
-                    ex = __ldg(rw + p.S_pad + (lane & 15));
-                }
-                if (is_front) { cgj = gj + 1 + adv; cw[1] = m; }
-            }
-            if (ok && !is_front) cw[1] |= 1ull << t;
-            cw[0] = KEY_VALID | ((uint64_t)(uint32_t)cgj << 32) |
-                    ((MODEL == JTB_MODEL_BANK) ? 0ull : (uint64_t)(uint32_t)creg);
-            int is_new = 0;
-            if (ok) {
-                if (cgj >= gj_end) {
-                    // every :ok op of the shard is linearized -> VALID
-                    if (atomicExch(&p.shard_found[shard], 1) == 0) {
-                        if (atomicSub(&ctrl->n_undecided, 1) == 1) atomicCAS(&ctrl->stop, 0, 1);
+                    for (int i = 0; i < 4; ++i) {
+                        const uint64_t v = ldcg64(slot + KW + i);
+                        pbal[2 * i] = (int32_t)(uint32_t)v;
+                        pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
                     }
-                    ok = false;
-                } else {
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    *(volatile uint64_t*)slot = 0;  // slot consumed
+                    atomicAnd(&sh.ticket_mask, ~(1u << warp));
+                }
+                has_ticket = false;
+            } else if (lane == 0 && warp == 0) {
+                sh.polls++;
+            }
+        }
+        __syncthreads();  // (C) popped / donated entries have been read: pushes may reuse the space
+        if (exiting) break;
+
+        if (ready) {
+            if (lane == 0) atomicAdd(&sh.n_exp, 1u);
+            // ---------------- expand (warp-synchronous) ---------------------------------------------
+            const int gj = (int)((w[0] >> 32) & 0x3fffffffu);
+            const int32_t preg = (int32_t)(uint32_t)w[0];
+            const int32_t* row = p.rows + (size_t)gj * p.row_words;
+            const int32_t extra = __ldg(row + p.S_pad + (lane & 15));
+            const int fr_pos = __shfl_sync(0xffffffffu, extra, 8);
+            const int shard = __shfl_sync(0xffffffffu, extra, 9);
+            const int gj_end = __shfl_sync(0xffffffffu, extra, 10);
+            const int cls_base = __shfl_sync(0xffffffffu, extra, 11);
+            const int ncls = __shfl_sync(0xffffffffu, extra, 12);
+            const int rslot = __shfl_sync(0xffffffffu, extra, 13);
+            const bool shard_alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
+            int n_new_total = 0;
+
+            auto push_children = [&](bool is_new, const uint64_t (&cw)[KW], const int32_t (&cbal)[8]) {
+                const unsigned newm = __ballot_sync(0xffffffffu, is_new);
+                if (newm == 0) return;
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&sh.top, (unsigned)__popc(newm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (is_new) {
+                    uint64_t* e = &s_deque[(size_t)((base + __popc(newm & ((1u << lane) - 1))) & cap_mask) * EW];
+#pragma unroll
+                    for (int i = 0; i < KW; ++i) e[i] = cw[i];
+                    if constexpr (L::HAS_BAL) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            e[KW + i] = (uint64_t)(uint32_t)cbal[2 * i] | ((uint64_t)(uint32_t)cbal[2 * i + 1] << 32);
+                    }
+                }
+                n_new_total += __popc(newm);
+            };
+
+            // -- candidates: ops in the open slots
+            for (int r = 0; r < cand_rounds && shard_alive; ++r) {
+                const int t = r * 32 + lane;
+                const int opid = __ldg(row + t);
+                const bool cand = opid >= 0 && !((w[1] >> t) & 1ull);
+                int4 op = make_int4(OP_IMPOSSIBLE, 0, 0, 0);
+                if (cand) op = __ldg(p.ops + opid);
+                int32_t creg = preg;
+                int32_t cbal[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+                bool ok = cand && model_step<MODEL>(op, creg, cbal, p.read_bal, neg_ok != 0);
+                const bool is_front = t == rslot;
+                uint64_t cw[KW];
+#pragma unroll
+                for (int i = 0; i < KW; ++i) cw[i] = w[i];
+                int cgj = gj;
+                // frontier advance, warp-cooperative, for the child that linearizes the frontier op
+                const unsigned front_ok = __ballot_sync(0xffffffffu, ok && is_front);
+                if (front_ok) {
+                    uint64_t m = w[1];
+                    int adv = 0;
+                    const int32_t* rw = row;
+                    int32_t ex = extra;
+                    for (;;) {
+                        const int32_t word = __shfl_sync(0xffffffffu, ex, lane >> 2);
+                        const int sl = (word >> (8 * (lane & 3))) & 0xff;
+                        const bool setb = sl != 0xff && ((m >> sl) & 1ull);
+                        const unsigned peers = __match_any_sync(0xffffffffu, sl);
+                        const bool pass = setb && (peers & ((1u << lane) - 1)) == 0;
+                        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                        const int n = pm == 0xffffffffu ? 32 : __ffs(~pm) - 1;
+                        const uint64_t clr = (lane < n) ? (1ull << sl) : 0ull;
+                        const uint32_t clo = __reduce_or_sync(0xffffffffu, (uint32_t)clr);
+                        const uint32_t chi = __reduce_or_sync(0xffffffffu, (uint32_t)(clr >> 32));
+                        m &= ~((uint64_t)clo | ((uint64_t)chi << 32));
+                        adv += n;
+                        if (n < 32) break;
+                        rw += (size_t)32 * p.row_words;
+                        ex = __ldg(rw + p.S_pad + (lane & 15));
+                    }
+                    if (is_front) { cgj = gj + 1 + adv; cw[1] = m; }
+                }
+                if (ok && !is_front) cw[1] |= 1ull << t;
+                cw[0] = KEY_VALID | ((uint64_t)(uint32_t)cgj << 32) |
+                        ((MODEL == JTB_MODEL_BANK) ? 0ull : (uint64_t)(uint32_t)creg);
+                int is_new = 0;
+                if (ok) {
+                    if (cgj >= gj_end) {
+                        // every :ok op of the shard is linearized -> VALID
+                        if (atomicExch(&p.shard_found[shard], 1) == 0) {
+                            if (atomicSub(&ctrl->n_undecided, 1) == 1) atomicCAS(&ctrl->stop, 0, 1);
+                        }
+                    } else {
+                        int plen;
+                        const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen);
+                        my_probes++;
+                        my_max_probe = max(my_max_probe, plen);
+                        if (res < 0) {
+                            atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
+                            atomicCAS(&ctrl->stop, 0, 2);
+                        }
+                        is_new = res > 0;
+                        if (is_new && cgj > gj) {
+                            // witness bookkeeping: furthest frontier reached in this shard
+                            const unsigned long long wc = *(volatile unsigned long long*)&sh.wit_cache;
+                            if ((int)(wc >> 32) != shard || (int)(uint32_t)wc < cgj) {
+                                *(volatile unsigned long long*)&sh.wit_cache =
+                                    ((unsigned long long)(uint32_t)shard << 32) | (uint32_t)cgj;
+                                atomicMax(&p.shard_max_rank[shard], cgj);
+                            }
+                        }
+                    }
+                }
+                push_children(is_new != 0, cw, cbal);
+            }
+            // -- candidates: next member of each crashed-op class
+            for (int r = 0; r < cls_rounds && shard_alive; ++r) {
+                const int c = r * 32 + lane;
+                bool cand = c < ncls;
+                struct { int first, n, word, shift_width; } cr = {0, 0, 1, 0};
+                int4 cop = make_int4(OP_IMPOSSIBLE, 0, 0, 0);
+                if (cand) {
+                    const int4* q = reinterpret_cast<const int4*>(p.classes + cls_base + c);
+                    const int4 b = __ldg(q + 1);
+                    cop = __ldg(q);
+                    cr.first = b.x; cr.n = b.y; cr.word = b.z; cr.shift_width = b.w;
+                }
+                const int shift = cr.shift_width & 0xff, width = cr.shift_width >> 8;
+                uint64_t cw[KW];
+                uint64_t field = 0;
+#pragma unroll
+                for (int i = 0; i < KW; ++i) { cw[i] = w[i]; if (i == cr.word) field = w[i]; }
+                const int count = (int)((field >> shift) & ((1ull << width) - 1));
+                cand = cand && count < cr.n;
+                if (cand) cand = __ldg(p.cls_inv_pos + cr.first + count) < fr_pos;
+                int32_t creg = preg;
+                int32_t cbal[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+                const bool ok = cand && model_step<MODEL>(cop, creg, cbal, p.read_bal, neg_ok != 0);
+#pragma unroll
+                for (int i = 1; i < KW; ++i) if (i == cr.word) cw[i] += 1ull << shift;
+                cw[0] = KEY_VALID | ((uint64_t)(uint32_t)gj << 32) |
+                        ((MODEL == JTB_MODEL_BANK) ? 0ull : (uint64_t)(uint32_t)creg);
+                int is_new = 0;
+                if (ok) {
                     int plen;
                     const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen);
                     my_probes++;
                     my_max_probe = max(my_max_probe, plen);
                     if (res < 0) {
                         atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
-                        atomicExch(&ctrl->stop, 2);
+                        atomicCAS(&ctrl->stop, 0, 2);
                     }
                     is_new = res > 0;
-                    if (is_new && cgj > gj) {
-                        // witness bookkeeping: furthest frontier reached in this shard
-                        const unsigned long long wc = *(volatile unsigned long long*)&sh.wit_cache;
-                        if ((int)(wc >> 32) != shard || (int)(uint32_t)wc < cgj) {
-                            *(volatile unsigned long long*)&sh.wit_cache =
-                                ((unsigned long long)(uint32_t)shard << 32) | (uint32_t)cgj;
-                            atomicMax(&p.shard_max_rank[shard], cgj);
-                        }
+                }
+                push_children(is_new != 0, cw, cbal);
+            }
+            if (lane == 0) {
+                if (n_new_total) atomicAdd(&sh.n_new, (unsigned)n_new_total);
+                my_expansions++;
+                my_configs += n_new_total;
+                if (++my_steps >= 32 || my_configs >= 512) {
+                    // amortised global tally: budget (max_configs) and table-load guard
+                    my_steps = 0;
+                    const unsigned long long tot = atomicAdd(&ctrl->configs, my_configs) + my_configs;
+                    my_configs = 0;
+                    if (tot >= p.max_configs) {
+                        atomicCAS(&ctrl->cause, 0, p.budget_cause);
+                        atomicCAS(&ctrl->stop, 0, 2);
                     }
                 }
             }
-            n_probe_total += ok ? 1 : 0;
-            push_children(is_new != 0, cw, cbal);
         }
-        // -- candidates: next member of each crashed-op class
-        for (int r = 0; r < cls_rounds; ++r) {
-            const int c = r * 32 + lane;
-            bool cand = c < ncls;
-            struct { int first, n, word, shift_width; } cr = {0, 0, 1, 0};
-            int4 cop = make_int4(OP_IMPOSSIBLE, 0, 0, 0);
-            if (cand) {
-                const int4* q = reinterpret_cast<const int4*>(p.classes + cls_base + c);
-                const int4 b = __ldg(q + 1);
-                cop = __ldg(q);
-                cr.first = b.x; cr.n = b.y; cr.word = b.z; cr.shift_width = b.w;
-            }
-            const int shift = cr.shift_width & 0xff, width = cr.shift_width >> 8;
-            uint64_t cw[KW];
-            uint64_t field = 0;
-#pragma unroll
-            for (int i = 0; i < KW; ++i) { cw[i] = w[i]; if (i == cr.word) field = w[i]; }
-            const int count = (int)((field >> shift) & ((1ull << width) - 1));
-            cand = cand && count < cr.n;
-            if (cand) cand = __ldg(p.cls_inv_pos + cr.first + count) < fr_pos;
-            int32_t creg = preg;
-            int32_t cbal[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-            const bool ok = cand && model_step<MODEL>(cop, creg, cbal, p.read_bal, neg_ok != 0);
-#pragma unroll
-            for (int i = 1; i < KW; ++i) if (i == cr.word) cw[i] += 1ull << shift;
-            cw[0] = KEY_VALID | ((uint64_t)(uint32_t)gj << 32) |
-                    ((MODEL == JTB_MODEL_BANK) ? 0ull : (uint64_t)(uint32_t)creg);
-            int is_new = 0;
-            if (ok) {
-                int plen;
-                const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen);
-                my_probes++;
-                my_max_probe = max(my_max_probe, plen);
-                if (res < 0) {
-                    atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
-                    atomicExch(&ctrl->stop, 2);
-                }
-                is_new = res > 0;
-            }
-            push_children(is_new != 0, cw, cbal);
-        }
-        if (lane == 0) {
-            my_configs += n_new_total;
-            if (++my_steps >= 32 || my_configs >= 512) {
-                // amortised global tally: budget (max_configs) and table-load guard
-                my_steps = 0;
-                const unsigned long long tot = atomicAdd(&ctrl->configs, my_configs) + my_configs;
-                my_configs = 0;
-                if (tot >= p.max_configs) {
-                    atomicCAS(&ctrl->cause, 0, p.budget_cause);
-                    atomicCAS(&ctrl->stop, 0, 2);
-                }
-            }
-        }
-        (void)init_reg;
     }
     // ---- flush statistics -------------------------------------------------------------------------
     for (int o = 16; o > 0; o >>= 1) {
@@ -579,12 +591,40 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
     if (lane == 0) {
         atomicAdd(&ctrl->configs, my_configs);
         atomicAdd(&ctrl->probes, my_probes);
+        atomicAdd(&ctrl->expansions, my_expansions);
         atomicMax(&ctrl->max_probe_len, (unsigned long long)my_max_probe);
     }
-    if (tid == 0) {
-        atomicAdd(&ctrl->pool_pushes, sh.pool_pushes);
-        atomicAdd(&ctrl->pool_pops, sh.pool_pops);
-        atomicAdd(&ctrl->idle_spins, sh.idle_spins);
+    if (tid == 0) atomicAdd(&ctrl->polls, sh.polls);
+}
+
+// Pause/resume support: gathers the live entries (non-zero ring slots in [lo, hi)) of a paused search
+// into a fresh ring, in ring order per block (order is immaterial for correctness).
+template <int EW>
+__global__ void ring_compact_kernel(const uint64_t* __restrict__ old_ring, uint64_t old_mask, unsigned long long lo,
+                                    unsigned long long hi, uint64_t* __restrict__ new_ring, uint64_t new_mask,
+                                    unsigned long long* __restrict__ new_tail) {
+    for (unsigned long long i = lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < hi;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint64_t* src = old_ring + (i & old_mask) * EW;
+        if (src[0] == 0) continue;
+        const unsigned long long o = atomicAdd(new_tail, 1ull);
+        uint64_t* dst = new_ring + (o & new_mask) * EW;
+#pragma unroll
+        for (int k = 0; k < EW; ++k) dst[k] = src[k];
+    }
+}
+
+// Re-inserts every key of a full table into a larger one (table growth without losing work).
+template <int KW>
+__global__ void table_rehash_kernel(const uint64_t* __restrict__ old_table, uint64_t old_slots, uint64_t* new_table,
+                                    uint64_t new_mask) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t k[KW];
+#pragma unroll
+        for (int w = 0; w < KW; ++w) k[w] = old_table[i * KW + w];
+        if (k[0] == 0) continue;
+        int plen;
+        table_insert<KW>(new_table, new_mask, k, &plen);
     }
 }
 

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
-           "jtb_table_bench"]
+           "jtb_table_bench", "jtb_get_stats"]
 
 _lib = None
 _lock = threading.Lock()
@@ -166,6 +166,13 @@ class Context:
             "lowest_index": res.lowest_index, "highest_index": res.highest_index,
             "seconds": res.seconds_total, "seconds_kernel": res.seconds_kernel,
         }
+
+    def stats(self) -> dict:
+        out = (C.c_ulonglong * 16)()
+        lib().jtb_get_stats(C.c_void_p(self._h), out, 16)
+        names = ["configs", "probes", "expansions", "ring_tail", "ring_head", "idle_polls",
+                 "max_probe_len", "table_slots", "grid", "ring_entries", "attempts", "kernel_us"]
+        return {n: int(out[i]) for i, n in enumerate(names)}
 
     # ---- K2 microbenchmark ----------------------------------------------------------------------
     def table_bench(self, n_keys: int, variant: int = 0, rounds: int = 3) -> dict:

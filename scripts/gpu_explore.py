@@ -12,6 +12,7 @@ for think_ms, stale in ((20, False), (20, True), (10, False), (10, True), (5, Fa
         r = ctx.check_linearizable(h, m)
     key = f"bank_think{think_ms}_{'stale' if stale else 'valid'}"
     r.pop("shards")
+    r["stats"] = ctx.stats()
     r["configs_per_s"] = r["configs"] / r["seconds_kernel"]
     r["probes_per_s"] = r["probes"] / r["seconds_kernel"]
     r["algo_GBps"] = r["hbm_bytes_algorithmic"] / r["seconds_kernel"] / 1e9
