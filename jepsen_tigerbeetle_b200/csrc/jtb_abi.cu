@@ -257,7 +257,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.S_pad = P.S_pad;
             p.n_shards = n_shards;
             p.max_nc = P.max_nc;
-            const uint64_t load_guard = (uint64_t)(0.70 * (double)n_slots);
+            const uint64_t load_guard = (uint64_t)(0.50 * (double)n_slots);  // linear probing: keep chains short
             p.max_configs = load_guard;
             p.budget_cause = JTB_CAUSE_TABLE_FULL;
             if (ctx->opts.max_configs && ctx->opts.max_configs <= load_guard) {

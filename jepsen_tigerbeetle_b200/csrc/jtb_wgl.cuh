@@ -16,7 +16,9 @@
 //    CTA's shared-memory staging buffer.
 //  * Work distribution: depth-first locally, breadth-first globally, no locks.
 //      - each CTA keeps a LIFO deque in shared memory shared by its 8 warps (deep dives find the
-//        linearization of a valid history quickly);
+//        linearization of a valid history quickly).  A barrier-free variant with one private deque per
+//        warp was also measured: correct, but 1.5x slower (private stacks fragment the work: 100 M idle
+//        polls vs 6 M) even though bar.sync is the top stall reason of this version (ncu, profiles/);
 //      - an idle warp takes a read TICKET (ring position from atomicAdd(head)) on a global FIFO ring in HBM
 //        and polls that slot; head - tail > 0 is therefore the number of hungry warps;
 //      - a CTA whose deque is nearly full, or that sees hungry warps, donates its OLDEST entries with one
@@ -277,19 +279,28 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
     unsigned long long my_configs = 0, my_probes = 0, my_expansions = 0;
     int my_steps = 0, my_max_probe = 0;
     bool exiting = false;
+    unsigned acc_new = 0, acc_exp = 0, acc_age = 0;  // thread 0 only
 
     for (;;) {
         __syncthreads();  // (A) pushes of the previous step are complete
         if (tid == 0) {
-            // ---- account the previous step: created before expanded (termination invariant) --------
-            if (sh.n_new) { atomicAdd(&ctrl->created, (unsigned long long)sh.n_new); __threadfence(); }
-            if (sh.n_exp) atomicAdd(&ctrl->expanded, (unsigned long long)sh.n_exp);
+            // ---- account the previous step (batched: only termination detection needs these) ---------
+            acc_new += sh.n_new;
+            acc_exp += sh.n_exp;
             const bool was_idle = sh.n_exp == 0;
             sh.n_exp = 0; sh.n_new = 0;
             int stop = ld_volatile(&ctrl->stop);
             const unsigned long long h = ld_volatile(&ctrl->head);
             const unsigned long long t = ld_volatile(&ctrl->tail);
             const unsigned size = sh.top - sh.bot;
+            // Invariant: an entry is counted in `created` before any other CTA can see it, and `created`
+            // is always advanced before `expanded`.  So flush before donating, when idle, and periodically.
+            const bool may_donate = stop == 2 || size > high || (h > t && size > 1);
+            if ((acc_new | acc_exp) && (may_donate || (was_idle && size == 0) || ++acc_age >= 16)) {
+                if (acc_new) { atomicAdd(&ctrl->created, (unsigned long long)acc_new); __threadfence(); }
+                if (acc_exp) atomicAdd(&ctrl->expanded, (unsigned long long)acc_exp);
+                acc_new = acc_exp = 0; acc_age = 0;
+            }
             if (stop == 0) {
                 if (t > h && t - h > p.ring_guard) {  // ring nearly full: pause (flush happens next step)
                     atomicCAS(&ctrl->cause, 0, CAUSE_RING_FULL);
