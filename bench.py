@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on the reference's headline config.
+
+metric   : configs explored/sec (BASELINE.json; time-to-verdict reported beside it)
+workload : BASELINE config #3 — 10k-op bank-transfer history, 32 clients, single B200
+           (synthetic, linearizable by construction; tau_op 10 ms, tau_think 5 ms, seed 1).
+           One "step" = one complete linearizability check of that history through the C ABI.
+           N > 1 : one such history per GPU as independent keys (ledgers), sharded by key, verdicts
+           merged with one NCCL all_reduce(MAX)  -> weak scaling.
+
+value    = configs / device time of the search kernels (CUDA events on the library's stream; inputs
+           already in HBM)            e2e = configs / wall time of the C-ABI call with HOST buffers
+           (flatten-prep, H2D, table clear, kernels, D2H verdict inside the timed region).
+
+--impl reference : the CPU restatement of knossos.wgl (oracle/, kind "port" — the reference's own
+           implementation is JVM-only and cannot run here) on the same history, each step a bounded
+           sample (first --ref-configs configurations), single thread like knossos.wgl.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from jepsen_tigerbeetle_b200 import history as H  # noqa: E402
+from jepsen_tigerbeetle_b200 import synth  # noqa: E402
+
+METRIC = "configs explored/sec (time-to-verdict alongside) on 10k-op/32-client bank history"
+UNIT = "configs/s"
+
+
+def workload(seed, args):
+    spec = synth.SynthSpec("bank", args.ops, args.clients, seed, tau_think_ns=args.think_ms * 1e6,
+                           stale_read=args.invalid)
+    return synth.generate(spec)
+
+
+def config_block(args, n_gpus):
+    return {"workload": f"C3 bank-transfer history: {args.ops} ops, {args.clients} clients, 8 accounts, "
+                        f"tau_op 10 ms, tau_think {args.think_ms} ms, seed 1+key, "
+                        f"{'one stale read (invalid)' if args.invalid else 'linearizable (valid)'}",
+            "keys": n_gpus, "sharding": "one key (ledger) per GPU" if n_gpus > 1 else "single key",
+            "l2": "visited table (>= 1 GiB, cleared every step) and 192 MiB work ring exceed the 126 MB L2",
+            "model": "bank", "table": "16 B slots, linear probing, load <= 0.5"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "of fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile():
+    p = os.path.join(ROOT, "profiles", "bench_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:  # noqa: BLE001
+            pass
+    return None
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    h = workload(1, args)
+    m = H.make_model(H.MODEL_BANK, accounts=range(1, 9))
+    cores = 1  # knossos.wgl searches one history on one thread
+    for _ in range(args.warmup):
+        oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_configs)
+    configs, secs = 0, 0.0
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        r = oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_configs)
+        secs += time.perf_counter() - t
+        configs += r["configs"]
+    v = configs / secs
+    sample = (f"first {args.ref_configs} configurations of the same history per step "
+              f"(single thread, like knossos.wgl; {os.cpu_count()} host cores present)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic", "config": config_block(args, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of knossos.wgl (oracle/lin_oracle.cpp); JVM Knossos cannot run here",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ops", type=int, default=10000)
+    ap.add_argument("--clients", type=int, default=32)
+    ap.add_argument("--think-ms", type=float, default=5.0)
+    ap.add_argument("--invalid", action="store_true", help="one stale read: exhaustive search, verdict invalid")
+    ap.add_argument("--ref-configs", type=int, default=3_000_000)
+    ap.add_argument("--cpu-baseline-configs", type=int, default=10_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from jepsen_tigerbeetle_b200 import distributed, native
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the checker has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    n_keys = max(1, world)
+    parts = [workload(1 + k, args) for k in range(n_keys)]
+    h_all = H.concat_keys(parts) if n_keys > 1 else parts[0]
+    m = H.make_model(H.MODEL_BANK, accounts=range(1, 9))
+    ctx = native.Context(device=local_rank)
+    reduce_max = distributed.torch_all_reduce_max(dev) if world > 1 else None
+    last = {}
+
+    def check_fn(sub):
+        r = ctx.check_linearizable(sub, m)
+        last.update(r)
+        last["stats"] = ctx.stats()
+        return r["shards"]
+
+    def step():
+        return distributed.check_sharded(h_all, check_fn, rank, world, reduce_max)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    kern_s, configs, probes, algo_bytes, launches, h2d, d2h = 0.0, 0, 0, 0, 0, 0, 0
+    verdict = None
+    for _ in range(args.steps):
+        out = step()
+        verdict = out["valid"]
+        kern_s += last["seconds_kernel"]
+        configs += last["configs"]; probes += last["probes"]; algo_bytes += last["hbm_bytes_algorithmic"]
+        launches += last["stats"]["kernel_launches"]; h2d += last["stats"]["h2d_bytes"]; d2h += last["stats"]["d2h_bytes"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # max over ranks of the times, sum over ranks of the work
+    agg = torch.tensor([kern_s, wall], dtype=torch.float64, device=dev)
+    tot = torch.tensor([configs, probes, algo_bytes, launches, h2d, d2h], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    kern_max, wall_max = (float(x) for x in agg.cpu())
+    configs_t, probes_t, bytes_t, launches_t, h2d_t, d2h_t = (float(x) for x in tot.cpu())
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        achieved = bytes_t / world / kern_max / 1e9  # per GPU, GB/s (algorithmic bytes / launch time)
+        tr = traffic_from_profile()
+        line = {
+            "metric": METRIC, "value": configs_t / kern_max, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic", "config": config_block(args, n_keys),
+            "verdict": {0: "valid", 1: "unknown", 2: "invalid"}[verdict],
+            "time_to_verdict_s": wall_max / args.steps, "time_to_verdict_kernel_s": kern_max / args.steps,
+            "configs_per_step": configs_t / args.steps, "probes_per_step": probes_t / args.steps,
+            "probes_per_s": probes_t / kern_max,
+            "e2e": {"value": configs_t / wall_max, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d_t / args.steps, "d2h_bytes_per_step": d2h_t / args.steps},
+            "gpu_launches": int(launches_t),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                         "peak_source": peak_src, "kernel": "wgl_search_kernel<bank,KW=2>",
+                         "algorithmic_bytes": "16 B x (probes + inserts) per launch (SURVEY 8(d))",
+                         "random_probe_ceiling_GBps": tr.get("table_probe_algo_GBps") if tr else None},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            t = time.perf_counter()
+            r = oracle.check_linearizable(parts[0], m, oracle.ALGO_WGL_COMPACT, max_configs=args.cpu_baseline_configs)
+            dt = time.perf_counter() - t
+            line["cpu_baseline"] = {
+                "value": r["configs"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"first {r['configs']} configurations of the same history, single thread "
+                          f"(knossos.wgl is single-threaded per history); {os.cpu_count()} host cores present",
+                "seconds": dt}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -218,7 +218,8 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
 
 /* ---- diagnostics: counters of the last jtb_check_linearizable call ------------------------------ *
  * out[0..11] = configs, probes, expansions, ring tail, ring head, idle polls, max probe length,
- * table slots, grid CTAs, ring entries, kernel launches (pause/resume growth + 1), kernel microseconds */
+ * table slots, grid CTAs, ring entries, search launches (pause/resume growth + 1), kernel microseconds,
+ * out[12..14] = host->device bytes, device->host bytes, CUDA kernels launched */
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n);
 
 /* ---- K2 in isolation: visited-table probe/insert microbenchmark (roofline evidence) ----------- *

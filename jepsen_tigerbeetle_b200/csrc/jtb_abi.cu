@@ -63,6 +63,7 @@ int ensure(jtb_ctx* ctx, DevBuf& b, size_t bytes) {
 
 template <typename T>
 int upload(jtb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
+    ctx->stats[12] += v.size() * sizeof(T);  // host -> device bytes of this call
     if (ensure(ctx, b, v.size() * sizeof(T) + 64)) return -1;
     if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     return 0;
@@ -187,6 +188,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     double kernel_s = 0;
     uint64_t configs = 0, probes = 0;
     ctx->stats[10] = 0;
+    ctx->stats[12] = ctx->stats[13] = ctx->stats[14] = 0;
     Ctrl hc;
     std::memset(&hc, 0, sizeof hc);
     std::vector<int> h_found(n_shards, 0), h_max(n_shards, 0);
@@ -321,6 +323,9 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             st[4] = hc.head; st[5] = hc.polls; st[6] = hc.max_probe_len; st[7] = n_slots;
             st[8] = (unsigned long long)grid; st[9] = ring_entries; st[10] = (unsigned long long)attempts;
             st[11] = (unsigned long long)(ms * 1e3);
+            st[12] += init_entries.size() * 8 + sizeof(Ctrl) + (size_t)n_shards * 4;
+            st[13] = (unsigned long long)attempts * sizeof(Ctrl) + (size_t)n_shards * 8;  // device -> host bytes
+            st[14] = (unsigned long long)(attempts + 2 * (attempts - 1));  // search launches + compact/rehash launches
         }
         if (hc.stop == 2 && hc.cause == CAUSE_RING_FULL) hc.cause = JTB_CAUSE_BUDGET;
         for (int s : searchable) {

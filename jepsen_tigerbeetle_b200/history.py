@@ -88,6 +88,34 @@ class FlatHistory:
         assert self.shard_off[-1] == n and np.all(np.diff(self.shard_off) >= 0)
         assert self.key_ids.dtype == np.int64 and self.key_ids.shape == (self.n_shards,)
 
+    def select_shards(self, shards: Sequence[int]) -> "FlatHistory":
+        """The sub-history made of the given shards (in that order) — what one rank of a multi-GPU
+        check receives.  Events keep their original :index, so witnesses stay globally meaningful."""
+        shards = [int(s) for s in shards]
+        lo = self.shard_off[shards] if shards else np.zeros(0, np.int64)
+        hi = self.shard_off[[s + 1 for s in shards]] if shards else np.zeros(0, np.int64)
+        counts = (hi - lo).astype(np.int64)
+        ev = (np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in zip(lo, hi)])
+              if shards else np.zeros(0, np.int64))
+        plen = np.maximum(self.payload_len[ev], 0).astype(np.int64)
+        new_off = np.zeros(ev.shape[0], np.int64)
+        if ev.shape[0]:
+            np.cumsum(plen[:-1], out=new_off[1:])
+        total = int(plen.sum())
+        payload = np.zeros(total, np.int32)
+        if total:
+            # gather payload ranges: index = old_off[event] + position inside the event's payload
+            rep = np.repeat(np.arange(ev.shape[0]), plen)
+            inner = np.arange(total, dtype=np.int64) - np.repeat(new_off, plen)
+            payload = self.payload[self.payload_off[ev][rep] + inner].astype(np.int32)
+        shard_off = np.zeros(len(shards) + 1, np.int64)
+        np.cumsum(counts, out=shard_off[1:])
+        return FlatHistory(self.type[ev], self.f[ev], self.flags[ev], self.process[ev], self.index[ev],
+                           self.time_ns[ev], self.a[ev], self.b[ev], self.c[ev], new_off,
+                           self.payload_len[ev], payload, shard_off,
+                           self.key_ids[shards].astype(np.int64) if shards else np.zeros(0, np.int64),
+                           dict(self.meta))
+
     def shard(self, s: int) -> "FlatHistory":
         """A single-shard view (copy) — `independent/subhistory` for key s."""
         lo, hi = int(self.shard_off[s]), int(self.shard_off[s + 1])
@@ -104,6 +132,22 @@ class FlatHistory:
                            self.payload_len[sl].copy(), payload.astype(np.int32),
                            np.array([0, hi - lo], np.int64), self.key_ids[s:s + 1].copy(),
                            dict(self.meta))
+
+
+def concat_keys(parts: Sequence[FlatHistory]) -> FlatHistory:
+    """Several single-key histories as ONE keyed history (shard s = parts[s], key id s + 1) — the shape
+    `independent/checker` sees when every ledger/key has its own sub-history."""
+    cat = lambda name: np.concatenate([getattr(p, name) for p in parts])  # noqa: E731
+    poff, base = [], 0
+    for p in parts:
+        poff.append(p.payload_off + base)
+        base += int(p.payload.shape[0])
+    shard_off = np.zeros(len(parts) + 1, np.int64)
+    np.cumsum([p.n_events for p in parts], out=shard_off[1:])
+    return FlatHistory(cat("type"), cat("f"), cat("flags"), cat("process"), cat("index"), cat("time_ns"),
+                       cat("a"), cat("b"), cat("c"), np.concatenate(poff).astype(np.int64), cat("payload_len"),
+                       cat("payload"), shard_off, np.arange(1, len(parts) + 1, dtype=np.int64),
+                       dict(parts[0].meta) if parts else {})
 
 
 class CHistory(ctypes.Structure):

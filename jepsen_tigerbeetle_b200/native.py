@@ -171,7 +171,8 @@ class Context:
         out = (C.c_ulonglong * 16)()
         lib().jtb_get_stats(C.c_void_p(self._h), out, 16)
         names = ["configs", "probes", "expansions", "ring_tail", "ring_head", "idle_polls",
-                 "max_probe_len", "table_slots", "grid", "ring_entries", "attempts", "kernel_us"]
+                 "max_probe_len", "table_slots", "grid", "ring_entries", "attempts", "kernel_us",
+                 "h2d_bytes", "d2h_bytes", "kernel_launches"]
         return {n: int(out[i]) for i, n in enumerate(names)}
 
     # ---- K2 microbenchmark ----------------------------------------------------------------------
