@@ -143,7 +143,7 @@ typedef struct jtb_lin_result {
 typedef struct jtb_setfull_shard {
     int32_t valid;
     int32_t attempt_count, stable_count, lost_count, never_read_count, stale_count, duplicated_count;
-    int32_t reserved0;
+    int32_t suspect_final_reads;   /* read-all-invoked-adds: :final? :ok reads missing an invoked add   */
     int64_t stable_latency_max_ms; /* max stable-latency (0 if none)  */
     int64_t lost_latency_max_ms;   /* max lost-latency (0 if none)    */
 } jtb_setfull_shard;
@@ -166,6 +166,18 @@ typedef struct jtb_setfull_out {
     int32_t  n_failures;
     double   seconds_kernel;
     double   seconds_total;
+    /* (read-all-invoked-adds), workloads/set_full.clj:51-75, evaluated in the same pass: every
+     * :final? :ok read must contain every :add value ever invoked in its sub-history.  Optional detail
+     * (CSR: suspect read -> missing element ids), caller-allocated:                                   */
+    int64_t  suspect_capacity;     /* capacity of suspect_shard / suspect_index (0 = not wanted)       */
+    int32_t* suspect_shard;
+    int32_t* suspect_index;        /* :index of the suspect final read                                 */
+    int64_t* suspect_missing_off;  /* [suspect_capacity + 1]                                           */
+    int64_t  missing_capacity;
+    int32_t* missing_ids;
+    int64_t  n_suspect;            /* out: total suspect final reads                                   */
+    int32_t  raia_valid;           /* out: JTB_VALID or JTB_INVALID                                    */
+    int32_t  reserved1;
 } jtb_setfull_out;
 
 /* bank SI checker (tests/ledger.clj:127-192) error classes, in `cond` precedence order */
@@ -196,6 +208,10 @@ typedef struct jtb_ctx jtb_ctx;
 
 /* ---- lifecycle -------------------------------------------------------------------------------- */
 int         jtb_abi_version(void);
+/* sizeof of the ABI structs as this library was compiled, for binding self-checks:
+ * 0 jtb_history, 1 jtb_model, 2 jtb_opts, 3 jtb_lin_shard, 4 jtb_lin_result, 5 jtb_setfull_shard,
+ * 6 jtb_setfull_out, 7 jtb_bank_result; -1 otherwise */
+long        jtb_struct_size(int which);
 int         jtb_device_count(void);                 /* number of CUDA devices, <0 on error          */
 jtb_ctx*    jtb_create(const jtb_opts* opts);       /* NULL on failure (no CUDA device etc.)        */
 void        jtb_destroy(jtb_ctx* ctx);

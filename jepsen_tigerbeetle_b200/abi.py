@@ -38,7 +38,7 @@ class CSetFullShard(C.Structure):
     _fields_ = [("valid", C.c_int32), ("attempt_count", C.c_int32), ("stable_count", C.c_int32),
                 ("lost_count", C.c_int32), ("never_read_count", C.c_int32),
                 ("stale_count", C.c_int32), ("duplicated_count", C.c_int32),
-                ("reserved0", C.c_int32), ("stable_latency_max_ms", C.c_int64),
+                ("suspect_final_reads", C.c_int32), ("stable_latency_max_ms", C.c_int64),
                 ("lost_latency_max_ms", C.c_int64)]
 
 
@@ -47,7 +47,11 @@ class CSetFullOut(C.Structure):
                 ("elem_id", C.c_void_p), ("elem_outcome", C.c_void_p),
                 ("elem_latency_ms", C.c_void_p), ("elem_dup_count", C.c_void_p),
                 ("valid", C.c_int32), ("n_failures", C.c_int32), ("seconds_kernel", C.c_double),
-                ("seconds_total", C.c_double)]
+                ("seconds_total", C.c_double),
+                ("suspect_capacity", C.c_int64), ("suspect_shard", C.c_void_p),
+                ("suspect_index", C.c_void_p), ("suspect_missing_off", C.c_void_p),
+                ("missing_capacity", C.c_int64), ("missing_ids", C.c_void_p),
+                ("n_suspect", C.c_int64), ("raia_valid", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class CBankResult(C.Structure):
@@ -59,3 +63,49 @@ class CBankResult(C.Structure):
                 ("highest_total", C.c_int64), ("lowest_index", C.c_int32),
                 ("highest_index", C.c_int32), ("seconds_kernel", C.c_double),
                 ("seconds_total", C.c_double)]
+
+
+def alloc_setfull_out(h, shards):
+    """Caller-side buffers for jtb_check_set_full (returns the struct and the numpy arrays backing it)."""
+    import numpy as np
+    n_add_inv = int(np.count_nonzero((h.f == 3) & (h.type == 0))) + 1
+    n_final = int(np.count_nonzero((h.flags & 1) != 0)) + 1
+    bufs = {
+        "elem_off": np.zeros(h.n_shards + 1, np.int64), "elem_id": np.zeros(n_add_inv, np.int32),
+        "elem_outcome": np.zeros(n_add_inv, np.uint8), "elem_latency_ms": np.zeros(n_add_inv, np.int64),
+        "elem_dup_count": np.zeros(n_add_inv, np.int32),
+        "suspect_shard": np.zeros(n_final, np.int32), "suspect_index": np.zeros(n_final, np.int32),
+        "suspect_missing_off": np.zeros(n_final + 1, np.int64),
+        "missing_ids": np.zeros(max(1, min(n_final * n_add_inv, 1 << 26)), np.int32),
+    }
+    out = CSetFullOut()
+    out.shards = C.cast(shards, C.c_void_p)
+    out.elem_capacity = n_add_inv
+    for k in ("elem_off", "elem_id", "elem_outcome", "elem_latency_ms", "elem_dup_count", "suspect_shard",
+              "suspect_index", "suspect_missing_off", "missing_ids"):
+        setattr(out, k, bufs[k].ctypes.data)
+    out.suspect_capacity = n_final
+    out.missing_capacity = bufs["missing_ids"].shape[0]
+    return out, bufs
+
+
+SETFULL_SHARD_FIELDS = ("valid", "attempt_count", "stable_count", "lost_count", "never_read_count", "stale_count",
+                        "duplicated_count", "suspect_final_reads", "stable_latency_max_ms", "lost_latency_max_ms")
+
+
+def setfull_to_dict(out, shards, bufs) -> dict:
+    n = int(bufs["elem_off"][-1])
+    ns = int(out.n_suspect)
+    moff = bufs["suspect_missing_off"]
+    return {
+        "valid": out.valid, "n_failures": out.n_failures, "seconds": out.seconds_total,
+        "seconds_kernel": out.seconds_kernel,
+        "shards": [{f: getattr(s, f) for f in SETFULL_SHARD_FIELDS} for s in shards],
+        "elem_off": bufs["elem_off"].copy(), "elem_id": bufs["elem_id"][:n].copy(),
+        "elem_outcome": bufs["elem_outcome"][:n].copy(), "elem_latency_ms": bufs["elem_latency_ms"][:n].copy(),
+        "elem_dup_count": bufs["elem_dup_count"][:n].copy(),
+        "raia_valid": out.raia_valid,
+        "suspect_final_reads": [
+            {"shard": int(bufs["suspect_shard"][i]), "index": int(bufs["suspect_index"][i]),
+             "missing": [int(x) for x in bufs["missing_ids"][int(moff[i]):int(moff[i + 1])]]} for i in range(ns)],
+    }

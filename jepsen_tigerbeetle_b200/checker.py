@@ -174,6 +174,30 @@ class SetFull(Checker, _Native):
         r = self.ctx.check_set_full(h, self.linearizable)
         return {"valid?": VERDICT_NAME[r["valid"]], "seconds-kernel": r["seconds_kernel"]}, self.shard_maps(r)
 
+
+class ReadAllInvokedAdds(Checker, _Native):
+    """`(read-all-invoked-adds)` — workloads/set_full.clj:51-75: every :final? :ok read must contain every
+    :add value invoked in its sub-history; else {:valid? false :suspect-final-reads [[index missing] ...]}.
+    Evaluated on the device in the same pass as set-full (shares its read x element bit-matrix)."""
+
+    def __init__(self, ctx: Context | None = None, **ctx_opts) -> None:
+        _Native.__init__(self, ctx, **ctx_opts)
+
+    def check_flat(self, test, h: FlatHistory) -> tuple[dict, list[dict]]:
+        r = self.ctx.check_set_full(h, True)
+        per = [{"valid?": True} for _ in range(h.n_shards)]
+        for sus in r["suspect_final_reads"]:
+            m = per[sus["shard"]]
+            m["valid?"] = False
+            m.setdefault("suspect-final-reads", []).append([sus["index"], sorted(sus["missing"])])
+        return {"valid?": r["raia_valid"] == VALID}, per
+
+    def check(self, test, history, opts=None) -> dict:
+        h = _flat(history, "set")
+        if h.n_shards != 1:
+            raise ValueError("history has independent keys: wrap with independent_checker(...)")
+        return self.check_flat(test, h)[1][0]
+
     def check(self, test, history, opts=None) -> dict:
         h = _flat(history, "set")
         if h.n_shards != 1:
@@ -245,7 +269,7 @@ class Independent(Checker):
         return "set"
 
     def _per_key(self, checker: Checker, test, h: FlatHistory, opts) -> list[dict]:
-        if isinstance(checker, (Linearizable, SetFull)):
+        if isinstance(checker, (Linearizable, SetFull, ReadAllInvokedAdds)):
             try:
                 return checker.check_flat(test, h)[1]
             except Exception:  # noqa: BLE001
@@ -282,6 +306,11 @@ def linearizable(opts: Mapping[str, Any], **kw) -> Linearizable:
 def set_full(opts: Mapping[str, Any] | None = None, **kw) -> SetFull:
     """`(checker/set-full {:linearizable? true})` — set_full.clj:157"""
     return SetFull(opts, **kw)
+
+
+def read_all_invoked_adds(**kw) -> ReadAllInvokedAdds:
+    """`(read-all-invoked-adds)` — set_full.clj:51-75, :158"""
+    return ReadAllInvokedAdds(**kw)
 
 
 def bank_checker(opts: Mapping[str, Any] | None = None, **kw) -> BankTotals:

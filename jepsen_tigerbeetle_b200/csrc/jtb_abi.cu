@@ -28,11 +28,12 @@ struct jtb_ctx {
     std::string err;
     std::mutex mu;  // a context serialises its calls; use one context per JVM thread for concurrency
     // cached device buffers (grown on demand, reused across calls)
-    DevBuf table, pool, rows, ops, read_bal, classes, cls_inv, ctrl, found, maxrank, scratch[8];
+    DevBuf table, pool, rows, ops, read_bal, set_need, classes, cls_inv, ctrl, found, maxrank, scratch[8];
     // pinned staging
     void* pin = nullptr;
     size_t pin_cap = 0;
     unsigned long long stats[16] = {0};
+    unsigned long long last_configs = 0;  // configs of the previous search (sizes the next table)
 };
 
 namespace {
@@ -95,6 +96,20 @@ extern "C" {
 
 int jtb_abi_version(void) { return JTB_ABI_VERSION; }
 
+long jtb_struct_size(int which) {
+    switch (which) {
+    case 0: return sizeof(jtb_history);
+    case 1: return sizeof(jtb_model);
+    case 2: return sizeof(jtb_opts);
+    case 3: return sizeof(jtb_lin_shard);
+    case 4: return sizeof(jtb_lin_result);
+    case 5: return sizeof(jtb_setfull_shard);
+    case 6: return sizeof(jtb_setfull_out);
+    case 7: return sizeof(jtb_bank_result);
+    }
+    return -1;
+}
+
 int jtb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
@@ -125,7 +140,7 @@ jtb_ctx* jtb_create(const jtb_opts* opts) {
 void jtb_destroy(jtb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->table, &ctx->pool, &ctx->rows, &ctx->ops, &ctx->read_bal, &ctx->classes,
+    DevBuf* bufs[] = {&ctx->table, &ctx->pool, &ctx->rows, &ctx->ops, &ctx->read_bal, &ctx->set_need, &ctx->classes,
                       &ctx->cls_inv, &ctx->ctrl, &ctx->found, &ctx->maxrank};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -147,7 +162,8 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     std::lock_guard<std::mutex> lk(ctx->mu);
     const double t_start = now_s();
     CK(cudaSetDevice(ctx->device));
-    if (m->kind != JTB_MODEL_REGISTER && m->kind != JTB_MODEL_CAS_REGISTER && m->kind != JTB_MODEL_BANK) {
+    if (m->kind != JTB_MODEL_REGISTER && m->kind != JTB_MODEL_CAS_REGISTER && m->kind != JTB_MODEL_BANK &&
+        m->kind != JTB_MODEL_SET) {
         ctx->err = "model not supported by the device search";
         return -2;
     }
@@ -178,7 +194,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         searchable.push_back(s);
         std::vector<uint64_t> e(EW, 0);
         e[0] = KEY_VALID | ((uint64_t)(uint32_t)P.rank_base[s] << 32) |
-               (bank ? 0ull : (uint64_t)(uint32_t)m->init_value);
+               ((bank || m->kind == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)m->init_value);
         if (bank)
             for (int i = 0; i < 4; ++i)
                 e[KW + i] = (uint64_t)(uint32_t)m->init_balance[2 * i] |
@@ -193,7 +209,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     std::memset(&hc, 0, sizeof hc);
     std::vector<int> h_found(n_shards, 0), h_max(n_shards, 0);
     if (!searchable.empty()) {
-        if (upload(ctx, ctx->rows, P.rows) || upload(ctx, ctx->ops, P.ops) || upload(ctx, ctx->read_bal, P.read_bal) ||
+        if (upload(ctx, ctx->rows, P.rows) || upload(ctx, ctx->ops, P.ops) || upload(ctx, ctx->read_bal, P.read_bal) || upload(ctx, ctx->set_need, P.set_need) ||
             upload(ctx, ctx->classes, P.classes) || upload(ctx, ctx->cls_inv, P.cls_inv_pos))
             return -1;
         if (ensure(ctx, ctx->ctrl, sizeof(Ctrl)) || ensure(ctx, ctx->found, n_shards * sizeof(int)) ||
@@ -201,12 +217,11 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             return -1;
         // CTA deque / grid
         const int cand_rounds = P.S_pad / 32, cls_rounds = (P.max_nc + 31) / 32;
-        const uint32_t worst_push = WGL_WARPS * 32 * (cand_rounds + cls_rounds);
-        uint32_t deque_cap = 512;
-        while (deque_cap < 2 * worst_push) deque_cap <<= 1;
-        const uint32_t stage_cap = deque_cap;
+        const uint32_t worst_push = WGL_WARPS * WGL_G * 32 * (cand_rounds + cls_rounds);
+        uint32_t deque_cap = 1024;                       // fixed: a full deque overflows to the ring
+        while ((size_t)deque_cap * EW * 8 > 48 * 1024) deque_cap >>= 1;
+        const uint32_t stage_cap = std::max(deque_cap, worst_push);
         const size_t smem = (size_t)deque_cap * EW * 8;
-        if (smem > 200 * 1024) { ctx->err = "too many crashed-op classes for the shared-memory deque"; return -1; }
         int ctas_per_sm = (int)std::min<size_t>(4, (220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, ctas_per_sm);
         const int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;
@@ -223,7 +238,9 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         const size_t reserve = (size_t)4 << 30;
         size_t max_table = ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)64 << 30;
         max_table = std::min(max_table, ctx->table.cap + (free_b > reserve ? free_b - reserve : 0));
-        size_t table_bytes = std::min<size_t>(max_table, ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)1 << 30);
+        // start at 1 GiB, or at 4x what the previous call on this context ended up needing (warm context)
+        size_t start_bytes = std::max<size_t>((size_t)1 << 30, (size_t)ctx->last_configs * 4 * KW * 8);
+        size_t table_bytes = std::min<size_t>(max_table, ctx->opts.table_bytes ? ctx->opts.table_bytes : start_bytes);
         uint64_t n_slots = 1;
         while (n_slots * 2 * KW * 8 <= table_bytes) n_slots <<= 1;
         if (ensure(ctx, ctx->table, n_slots * KW * 8)) return -1;
@@ -245,6 +262,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.rows = (const int32_t*)ctx->rows.p;
             p.ops = (const int4*)ctx->ops.p;
             p.read_bal = (const int32_t*)ctx->read_bal.p;
+            p.set_need = (const uint64_t*)ctx->set_need.p;
             p.classes = (const ClassRec*)ctx->classes.p;
             p.cls_inv_pos = (const int32_t*)ctx->cls_inv.p;
             p.table = (uint64_t*)ctx->table.p;
@@ -270,6 +288,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.deque_cap = deque_cap;
             int rc;
             if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem);
+            else if (m->kind == JTB_MODEL_SET) rc = launch_wgl<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem);
             else rc = launch_wgl_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, grid, smem);
             if (rc) { free_tmp(); return rc; }
             CK(cudaMemcpyAsync(&hc, ctx->ctrl.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -317,6 +336,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         kernel_s = ms * 1e-3;
         configs = hc.configs;
         probes = hc.probes;
+        ctx->last_configs = hc.configs;
         {
             unsigned long long* st = ctx->stats;
             st[0] = hc.configs; st[1] = hc.probes; st[2] = hc.expansions; st[3] = hc.tail;

@@ -76,10 +76,110 @@ OpRec resolve(const jtb_history* h, const jtb_model* m, int64_t ev, Prepared& ou
             r.x |= OP_IMPOSSIBLE;
         }
         break;
+    case JTB_MODEL_SET:
+        // adds: y = element value for now (dense id assigned by build_set_tables); reads are completed
+        // by build_set_tables (per-(read, frontier) need/care masks)
+        r.y = h->a[ev];
+        if (f != JTB_F_ADD && f != JTB_F_READ) r.x |= OP_IMPOSSIBLE;
+        break;
     default:
         r.x |= OP_IMPOSSIBLE;
     }
     return r;
+}
+
+// Grow-only set (knossos.model/set): a read of V is consistent iff the elements of the linearized adds
+// are exactly V.  The linearized set is a function of the config, so the state needs no storage:
+// for every read rho and every frontier rank g at which rho can be a candidate we precompute
+//   need/care over key word 1  such that  rho is consistent  <=>  (word1 & care) == need.
+// Adds that returned before rho was invoked are always linearized (must all be in V); adds invoked
+// after rho returned never are; an overlapping add x must be linearized iff elem(x) in V:
+//   rank(x) < g            -> linearized (fine if required, fatal if forbidden)
+//   open at g (slot bit)   -> constrained bit
+//   not yet invoked at g   -> not linearized (fatal if required)
+// crashed adds contribute their 1-bit class count field the same way.
+// Returns false when the shard needs something this encoding cannot express (an element of V whose only
+// providers are two or more overlapping adds, or class fields outside word 1).
+bool build_set_tables(const jtb_history* h, ShardTmp& t, const std::vector<int32_t>& gid, int64_t rank_base,
+                      const std::vector<std::pair<int, int>>& field, const std::vector<int32_t>& fr_pos,
+                      Prepared& out) {
+    struct Add { int op; int32_t elem; bool crashed; int inv_pos, ret_pos, rank, slot, cls; };
+    std::vector<Add> adds;
+    for (int i = 0; i < (int)t.ops.size(); ++i) {
+        const HOp& o = t.ops[i];
+        const int64_t ev = o.crashed ? o.inv_ev : o.ret_ev;
+        if (h->f[ev] != JTB_F_ADD) continue;
+        adds.push_back(Add{i, h->a[ev], o.crashed, o.inv_pos, o.ret_pos, o.rank, o.slot, o.cls});
+    }
+    for (auto& f : field)
+        if (f.first != 1) return false;
+    for (auto& mem : t.cls_members)
+        if (mem.size() > 1) return false;  // the same element crashed twice: multi-provider
+    const int R = (int)t.rets.size();
+    for (int j = 0; j < R; ++j) {
+        const int i = t.rets[j];
+        const HOp& ro = t.ops[i];
+        if (h->f[ro.ret_ev] != JTB_F_READ) continue;
+        OpRec& rec = out.ops[gid[i]];
+        const int n = h->payload_len[ro.ret_ev];
+        if (n < 0) { rec.x |= OP_IMPOSSIBLE; continue; }
+        const int32_t* pl = h->payload + h->payload_off[ro.ret_ev];
+        std::vector<int32_t> V(pl, pl + n);
+        std::sort(V.begin(), V.end());
+        V.erase(std::unique(V.begin(), V.end()), V.end());
+        auto inV = [&](int32_t e) { return std::binary_search(V.begin(), V.end(), e); };
+        bool impossible = false;
+        std::vector<int32_t> covered;  // elements of V provided by adds that returned before rho's invoke
+        std::vector<const Add*> overlap;
+        for (const Add& x : adds) {
+            if (x.inv_pos >= ro.ret_pos) continue;                 // invoked after rho returned
+            if (!x.crashed && x.ret_pos < ro.inv_pos) {            // returned before rho was invoked
+                if (!inV(x.elem)) { impossible = true; break; }
+                covered.push_back(x.elem);
+            } else overlap.push_back(&x);
+        }
+        if (!impossible) {
+            std::sort(covered.begin(), covered.end());
+            // every element of V needs a provider; exactly one overlapping provider if not covered
+            for (int32_t e : V) {
+                if (std::binary_search(covered.begin(), covered.end(), e)) continue;
+                int providers = 0;
+                for (const Add* x : overlap) providers += x->elem == e;
+                if (providers == 0) { impossible = true; break; }
+                if (providers > 1) return false;
+            }
+        }
+        if (impossible) { rec.x |= OP_IMPOSSIBLE; continue; }
+        // first frontier rank at which rho is open: smallest g with fr_pos[g] > inv_pos(rho)
+        int g0 = (int)(std::upper_bound(fr_pos.begin(), fr_pos.end(), ro.inv_pos) - fr_pos.begin());
+        rec.y = (int32_t)(out.set_need.size() / 2);
+        rec.z = (int32_t)(rank_base + g0);
+        rec.w = (int32_t)(rank_base + j);
+        for (int g = g0; g <= j; ++g) {
+            uint64_t need = 0, care = 0;
+            bool feasible = true;
+            for (const Add* x : overlap) {
+                const bool covered_e = std::binary_search(covered.begin(), covered.end(), x->elem);
+                const bool want = inV(x->elem);
+                if (want && covered_e) continue;                    // unconstrained
+                if (x->crashed) {
+                    const uint64_t bit = 1ull << (field[x->cls].second & 0xff);
+                    if (x->inv_pos < fr_pos[g]) { care |= bit; if (want) need |= bit; }
+                    else if (want) feasible = false;
+                } else if (x->rank < g) {
+                    if (!want) feasible = false;                    // already linearized but not in V
+                } else if (x->inv_pos < fr_pos[g]) {
+                    const uint64_t bit = 1ull << x->slot;
+                    care |= bit;
+                    if (want) need |= bit;
+                } else if (want) feasible = false;                  // required but not invoked yet
+            }
+            if (!feasible) { need = ~0ull; care = 0; }              // (w & 0) == ~0 never holds
+            out.set_need.push_back(need);
+            out.set_need.push_back(care);
+        }
+    }
+    return true;
 }
 
 }  // namespace
@@ -265,6 +365,14 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
             row[out.S_pad + 15] = 0;
             out.ret_index[base + j] = h->index[ro.ret_ev];
             cur[ro.slot] = -1;  // the op has returned
+        }
+        if (m->kind == JTB_MODEL_SET) {
+            std::vector<int32_t> fr_pos(R);
+            for (int j = 0; j < R; ++j) fr_pos[j] = t.ops[t.rets[j]].ret_pos;
+            if (!build_set_tables(h, t, gid, base, field[s], fr_pos, out)) {
+                // not expressible: the shard is reported UNKNOWN (too wide); neutralise its rows
+                out.shard_cause[s] = JTB_CAUSE_TOO_WIDE;
+            }
         }
     }
     return true;

@@ -34,8 +34,9 @@ struct SfRead {        // one :ok read (device)
     int64_t inv_time, ok_time;
     int64_t pl_off;    // into payload
     int32_t pl_len;
-    int32_t shard;
+    int32_t shard;     // bit 31 set: :final? read
 };
+constexpr int32_t SF_FINAL_BIT = (int32_t)0x80000000;
 struct SfShard {       // device
     int64_t elem_off;  // into element arrays
     int32_t n_elems;
@@ -68,7 +69,7 @@ __global__ void sf_build_bits(const SfRead* __restrict__ reads, int64_t n_reads,
     const int lane = threadIdx.x & 31;
     if (r >= n_reads) return;
     const SfRead rd = reads[r];
-    const SfShard sd = shards[rd.shard];
+    const SfShard sd = shards[rd.shard & ~SF_FINAL_BIT];
     const SfElem* el = elems + sd.elem_off;
     uint32_t* rowbits = bits + sd.bits_off + (r - sd.read_off) * (int64_t)sd.words_per_row;
     bool dup = false;
@@ -90,6 +91,28 @@ __global__ void sf_build_bits(const SfRead* __restrict__ reads, int64_t n_reads,
     if (__any_sync(0xffffffffu, dup) && lane == 0) read_dup_flag[r] = 1;
 }
 
+// (read-all-invoked-adds) workloads/set_full.clj:51-75 on the same bit-matrix: a :final? :ok read is suspect
+// when any tracked element (= any value ever :add-invoked in the sub-history) is absent from it.
+// One warp per read; writes the number of missing elements (0 for non-final reads).
+__global__ void sf_final_missing(const SfRead* __restrict__ reads, int64_t n_reads, const SfShard* __restrict__ shards,
+                                 const uint32_t* __restrict__ bits, int* __restrict__ missing) {
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    const SfRead rd = reads[r];
+    if (!(rd.shard & SF_FINAL_BIT)) { if (lane == 0) missing[r] = 0; return; }
+    const SfShard sd = shards[rd.shard & ~SF_FINAL_BIT];
+    const uint32_t* rowbits = bits + sd.bits_off + (r - sd.read_off) * (int64_t)sd.words_per_row;
+    int zeros = 0;
+    for (int w = lane; w < sd.words_per_row; w += 32) {
+        const int valid_bits = min(32, sd.n_elems - w * 32);
+        const uint32_t m = valid_bits == 32 ? 0xffffffffu : ((1u << valid_bits) - 1);
+        zeros += __popc(~rowbits[w] & m);
+    }
+    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    if (lane == 0) missing[r] = zeros;
+}
+
 // exact multiplicities for the (rare) reads that contain a repeated element
 __global__ void sf_count_dups(const SfRead* __restrict__ reads, const int* __restrict__ flagged, int n_flagged,
                               const SfShard* __restrict__ shards, const SfElem* __restrict__ elems,
@@ -97,7 +120,7 @@ __global__ void sf_count_dups(const SfRead* __restrict__ reads, const int* __res
     const int r = flagged[blockIdx.x];
     if (blockIdx.x >= n_flagged) return;
     const SfRead rd = reads[r];
-    const SfShard sd = shards[rd.shard];
+    const SfShard sd = shards[rd.shard & ~SF_FINAL_BIT];
     const SfElem* el = elems + sd.elem_off;
     for (int i = threadIdx.x; i < rd.pl_len; i += blockDim.x) {
         const int32_t id = payload[rd.pl_off + i];
@@ -277,7 +300,7 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
                     r.ok_idx = h->index[e]; r.ok_time = h->time_ns[e];
                     r.pl_off = h->payload_off[e];
                     r.pl_len = std::max(0, (int)h->payload_len[e]);
-                    r.shard = s;
+                    r.shard = s | ((h->flags && (h->flags[e] & JTB_FLAG_FINAL)) ? SF_FINAL_BIT : 0);
                     reads.push_back(r);
                 }
             }
@@ -307,11 +330,11 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
     SfShard* d_shards = nullptr; SfElem* d_elems = nullptr; int32_t* d_elem_shard = nullptr; SfRead* d_reads = nullptr;
     int32_t* d_payload = nullptr; uint32_t* d_bits = nullptr; int* d_dupflag = nullptr; SfAcc* d_acc = nullptr;
     uint8_t* d_outcome = nullptr; long long* d_lat = nullptr; int* d_dup = nullptr; int32_t* d_id = nullptr;
-    SfShardOut* d_tally = nullptr; int* d_flagged = nullptr;
+    SfShardOut* d_tally = nullptr; int* d_flagged = nullptr; int* d_missing = nullptr;
     auto cleanup = [&]() {
         cudaFree(d_shards); cudaFree(d_elems); cudaFree(d_elem_shard); cudaFree(d_reads); cudaFree(d_payload);
         cudaFree(d_bits); cudaFree(d_dupflag); cudaFree(d_acc); cudaFree(d_outcome); cudaFree(d_lat); cudaFree(d_dup);
-        cudaFree(d_id); cudaFree(d_tally); cudaFree(d_flagged);
+        cudaFree(d_id); cudaFree(d_tally); cudaFree(d_flagged); cudaFree(d_missing);
     };
     auto nz = [](size_t b) { return b ? b : (size_t)16; };
     SCK(cudaMalloc(&d_shards, nz(n_shards * sizeof(SfShard))));
@@ -327,6 +350,8 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
     SCK(cudaMalloc(&d_dup, nz(n_elems * 4)));
     SCK(cudaMalloc(&d_id, nz(n_elems * 4)));
     SCK(cudaMalloc(&d_tally, nz(n_shards * sizeof(SfShardOut))));
+    SCK(cudaMalloc(&d_missing, nz(n_reads * 4)));
+    SCK(cudaMemsetAsync(d_missing, 0, nz(n_reads * 4), st));
     SCK(cudaMemcpyAsync(d_shards, shards.data(), n_shards * sizeof(SfShard), cudaMemcpyHostToDevice, st));
     SCK(cudaMemcpyAsync(d_elems, elems.data(), n_elems * sizeof(SfElem), cudaMemcpyHostToDevice, st));
     SCK(cudaMemcpyAsync(d_elem_shard, elem_shard.data(), n_elems * 4, cudaMemcpyHostToDevice, st));
@@ -349,6 +374,8 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
         for (auto& sd : shards) { max_e = std::max(max_e, sd.n_elems); max_r = std::max(max_r, sd.n_reads); }
         dim3 grid((max_e + 255) / 256, (max_r + SF_RCHUNK - 1) / SF_RCHUNK, n_shards);
         sf_column_scan<<<grid, 256, 0, st>>>(d_reads, d_shards, d_elems, d_bits, d_acc);
+        SCK(cudaGetLastError());
+        sf_final_missing<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_reads, n_reads, d_shards, d_bits, d_missing);
         SCK(cudaGetLastError());
         // duplicates (rare): exact multiplicities for flagged reads
         std::vector<int> flag((size_t)n_reads);
@@ -380,12 +407,47 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
     SCK(cudaStreamSynchronize(st));
     float ms = 0;
     SCK(cudaEventElapsedTime(&ms, e0, e1));
+    // read-all-invoked-adds: suspects = final reads with missing elements; ids enumerated from their bit rows
+    std::vector<int> h_missing((size_t)n_reads, 0);
+    if (n_reads > 0) SCK(cudaMemcpy(h_missing.data(), d_missing, n_reads * 4, cudaMemcpyDeviceToHost));
+    std::vector<int> suspect_per_shard(n_shards, 0);
+    out->n_suspect = 0;
+    out->raia_valid = JTB_VALID;
+    {
+        int64_t cursor = 0;
+        if (out->suspect_capacity > 0) out->suspect_missing_off[0] = 0;
+        std::vector<uint32_t> rowbits;
+        for (int64_t r = 0; r < n_reads; ++r) {
+            if (!h_missing[r]) continue;
+            const int s = reads[r].shard & ~SF_FINAL_BIT;
+            suspect_per_shard[s]++;
+            out->raia_valid = JTB_INVALID;
+            if (out->suspect_capacity > 0) {
+                if (out->n_suspect >= out->suspect_capacity || cursor + h_missing[r] > out->missing_capacity) {
+                    err = "suspect/missing capacity too small";
+                    cleanup();
+                    return -4;
+                }
+                const SfShard& sd = shards[s];
+                rowbits.resize(sd.words_per_row);
+                SCK(cudaMemcpy(rowbits.data(), d_bits + sd.bits_off + (r - sd.read_off) * (int64_t)sd.words_per_row,
+                               (size_t)sd.words_per_row * 4, cudaMemcpyDeviceToHost));
+                out->suspect_shard[out->n_suspect] = s;
+                out->suspect_index[out->n_suspect] = reads[r].ok_idx;
+                for (int e = 0; e < sd.n_elems; ++e)  // elems are sorted by id inside a shard
+                    if (!((rowbits[e >> 5] >> (e & 31)) & 1u)) out->missing_ids[cursor++] = elems[sd.elem_off + e].id;
+                out->suspect_missing_off[out->n_suspect + 1] = cursor;
+            }
+            out->n_suspect++;
+        }
+    }
     out->valid = JTB_VALID;
     out->n_failures = 0;
     if (out->elem_capacity > 0) out->elem_off[0] = 0;
     for (int s = 0; s < n_shards; ++s) {
         jtb_setfull_shard& r = out->shards[s];
         std::memset(&r, 0, sizeof r);
+        r.suspect_final_reads = suspect_per_shard[s];
         r.attempt_count = shards[s].n_elems;
         r.stable_count = tally[s].stable; r.lost_count = tally[s].lost; r.never_read_count = tally[s].never_read;
         r.stale_count = tally[s].stale; r.duplicated_count = tally[s].duplicated;

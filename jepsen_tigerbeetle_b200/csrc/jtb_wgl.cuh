@@ -62,6 +62,7 @@ struct WglParams {
     const int32_t* rows;
     const int4* ops;
     const int32_t* read_bal;
+    const uint64_t* set_need;   // set model: (need, care) pairs per (read, frontier rank)
     const ClassRec* classes;
     const int32_t* cls_inv_pos;
     uint64_t* table;        // slots of KW 64-bit words
@@ -184,7 +185,8 @@ __device__ __forceinline__ int table_insert(uint64_t* table, uint64_t slot_mask,
 // `bal` the 8 balances carried in the entry.
 template <int MODEL>
 __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t (&bal)[8],
-                                           const int32_t* __restrict__ read_bal, bool neg_ok) {
+                                           const int32_t* __restrict__ read_bal, bool neg_ok, int gj,
+                                           uint64_t w1, const uint64_t* __restrict__ set_need) {
     const int f = op.x & 0xff;
     if (op.x & OP_IMPOSSIBLE) return false;
     if constexpr (MODEL == JTB_MODEL_REGISTER || MODEL == JTB_MODEL_CAS_REGISTER) {
@@ -217,6 +219,12 @@ __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t 
         ok &= !(care & 64) || bal[6] == hi.z;
         ok &= !(care & 128) || bal[7] == hi.w;
         return ok;
+    } else if constexpr (MODEL == JTB_MODEL_SET) {
+        // grow-only set: adds always apply; a read is consistent iff the constrained bits of key word 1
+        // (open-slot mask + crashed-add counts) equal the precomputed pattern for this (read, frontier)
+        if (f == JTB_F_ADD) return true;
+        const ulonglong2 nc = __ldg(reinterpret_cast<const ulonglong2*>(set_need) + (op.y + (gj - op.z)));
+        return (w1 & nc.y) == nc.x;
     } else {
         return false;
     }
@@ -232,6 +240,7 @@ struct EntryLayout {
 constexpr int WGL_WARPS = 8;
 constexpr int WGL_THREADS = WGL_WARPS * 32;
 constexpr unsigned WGL_MAX_DONATE = 64;       // per step, when donating to hungry warps
+constexpr int WGL_G = 2;                      // local entries a warp expands per step (amortises the 3 barriers)
 
 struct CtaShared {
     int stop;
@@ -262,8 +271,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
     const int cand_rounds = p.S_pad / 32;
     const int cls_rounds = (p.max_nc + 31) / 32;
     const unsigned cap_mask = p.deque_cap - 1;
-    const unsigned worst_push = WGL_WARPS * 32 * (cand_rounds + cls_rounds);
-    const unsigned high = p.deque_cap - worst_push;
+    const unsigned high = p.deque_cap / 2;   // donate the oldest entries beyond this; overflow goes to the ring
 
     if (tid == 0) {
         sh.stop = 0; sh.top = sh.bot = 0;
@@ -280,6 +288,8 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
     int my_steps = 0, my_max_probe = 0;
     bool exiting = false;
     unsigned acc_new = 0, acc_exp = 0, acc_age = 0;  // thread 0 only
+    int pre_stop = 0;                                // thread 0 only: control words read one step ahead
+    unsigned long long pre_head = 0, pre_tail = 0;
 
     for (;;) {
         __syncthreads();  // (A) pushes of the previous step are complete
@@ -289,9 +299,8 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             acc_exp += sh.n_exp;
             const bool was_idle = sh.n_exp == 0;
             sh.n_exp = 0; sh.n_new = 0;
-            int stop = ld_volatile(&ctrl->stop);
-            const unsigned long long h = ld_volatile(&ctrl->head);
-            const unsigned long long t = ld_volatile(&ctrl->tail);
+            int stop = pre_stop;
+            const unsigned long long h = pre_head, t = pre_tail;   // prefetched during the last step
             const unsigned size = sh.top - sh.bot;
             // Invariant: an entry is counted in `created` before any other CTA can see it, and `created`
             // is always advanced before `expanded`.  So flush before donating, when idle, and periodically.
@@ -343,9 +352,13 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 sh.bot += n_don;
             }
             // ---- local pops go to warps that hold no ticket; the remaining ticketless warps take one ----
-            unsigned n_local = stop ? 0 : min(size - n_don, (unsigned)__popc(free_warps));
+            const unsigned n_free = (unsigned)__popc(free_warps);
+            unsigned n_local = stop ? 0 : min(size - n_don, n_free * WGL_G);
+            // the first min(n_local, n_free) free warps pop; warp with rank k among them takes entries
+            // k, k + n_poppers, ... (deepest first)
+            const unsigned n_poppers = min(n_local, n_free);
             unsigned local_mask = 0, rest = free_warps;
-            for (unsigned k = 0; k < n_local; ++k) { const unsigned b = rest & (0u - rest); local_mask |= b; rest ^= b; }
+            for (unsigned k = 0; k < n_poppers; ++k) { const unsigned b = rest & (0u - rest); local_mask |= b; rest ^= b; }
             sh.local_mask = local_mask;
             sh.n_local = n_local;
             sh.pop_top = sh.top;
@@ -375,23 +388,47 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
         // ---- fetch: a local entry, or poll my ring ticket ----------------------------------------------
         uint64_t w[KW];
         int32_t pbal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint64_t w2[WGL_G - 1][KW];            // further local entries of this step
+        int32_t pbal2[WGL_G - 1][8];
+        int n_mine = 0;
         bool ready = false;
         if ((sh.assign_mask >> warp) & 1u) {
             ticket = sh.ticket_base + __popc(sh.assign_mask & ((1u << warp) - 1));
             has_ticket = true;
         }
         if ((sh.local_mask >> warp) & 1u) {
-            const unsigned k = __popc(sh.local_mask & ((1u << warp) - 1));
-            const uint64_t* e = &s_deque[(size_t)((sh.pop_top - 1 - k) & cap_mask) * EW];
+            const unsigned k0 = __popc(sh.local_mask & ((1u << warp) - 1));
+            const unsigned n_poppers = __popc(sh.local_mask);
+            const unsigned n_local = sh.n_local;
 #pragma unroll
-            for (int i = 0; i < KW; ++i) w[i] = e[i];
-            if constexpr (L::HAS_BAL) {
+            for (int g = 0; g < WGL_G; ++g) {
+                const unsigned k = k0 + g * n_poppers;
+                if (k >= n_local) break;
+                const uint64_t* e = &s_deque[(size_t)((sh.pop_top - 1 - k) & cap_mask) * EW];
+                if (g == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint64_t v = e[KW + i];
-                    pbal[2 * i] = (int32_t)(uint32_t)v;
-                    pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+                    for (int i = 0; i < KW; ++i) w[i] = e[i];
+                    if constexpr (L::HAS_BAL) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t v = e[KW + i];
+                            pbal[2 * i] = (int32_t)(uint32_t)v;
+                            pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KW; ++i) w2[g - 1][i] = e[i];
+                    if constexpr (L::HAS_BAL) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t v = e[KW + i];
+                            pbal2[g - 1][2 * i] = (int32_t)(uint32_t)v;
+                            pbal2[g - 1][2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+                        }
+                    }
                 }
+                n_mine = g + 1;
             }
             ready = true;
         } else if (has_ticket && !exiting) {
@@ -422,8 +459,20 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
         }
         __syncthreads();  // (C) popped / donated entries have been read: pushes may reuse the space
         if (exiting) break;
+        if (tid == 0) {  // prefetch the control words of the NEXT step behind this step's expansions
+            pre_stop = ld_volatile(&ctrl->stop);
+            pre_head = ld_volatile(&ctrl->head);
+            pre_tail = ld_volatile(&ctrl->tail);
+        }
 
-        if (ready) {
+        if (ready && n_mine == 0) n_mine = 1;  // an entry served by my ring ticket
+        for (int g = 0; g < n_mine; ++g) {
+            if (g > 0) {
+#pragma unroll
+                for (int i = 0; i < KW; ++i) w[i] = w2[g - 1][i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pbal[i] = pbal2[g - 1][i];
+            }
             if (lane == 0) atomicAdd(&sh.n_exp, 1u);
             // ---------------- expand (warp-synchronous) ---------------------------------------------
             const int gj = (int)((w[0] >> 32) & 0x3fffffffu);
@@ -437,25 +486,61 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             const int ncls = __shfl_sync(0xffffffffu, extra, 12);
             const int rslot = __shfl_sync(0xffffffffu, extra, 13);
             const bool shard_alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
-            int n_new_total = 0;
+            int n_new_total = 0, n_new_local = 0;
 
             auto push_children = [&](bool is_new, const uint64_t (&cw)[KW], const int32_t (&cbal)[8]) {
                 const unsigned newm = __ballot_sync(0xffffffffu, is_new);
                 if (newm == 0) return;
+                const unsigned n = (unsigned)__popc(newm);
+                // reserve space on the CTA deque; if it is full, publish straight to the global ring
                 unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&sh.top, (unsigned)__popc(newm));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (is_new) {
-                    uint64_t* e = &s_deque[(size_t)((base + __popc(newm & ((1u << lane) - 1))) & cap_mask) * EW];
-#pragma unroll
-                    for (int i = 0; i < KW; ++i) e[i] = cw[i];
-                    if constexpr (L::HAS_BAL) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            e[KW + i] = (uint64_t)(uint32_t)cbal[2 * i] | ((uint64_t)(uint32_t)cbal[2 * i + 1] << 32);
+                int to_ring = 0;
+                if (lane == 0) {
+                    unsigned old = *(volatile unsigned*)&sh.top;
+                    for (;;) {
+                        if (old + n - sh.bot > p.deque_cap) { to_ring = 1; break; }
+                        const unsigned seen = atomicCAS(&sh.top, old, old + n);
+                        if (seen == old) { base = old; break; }
+                        old = seen;
                     }
                 }
-                n_new_total += __popc(newm);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                to_ring = __shfl_sync(0xffffffffu, to_ring, 0);
+                const unsigned my = __popc(newm & ((1u << lane) - 1));
+                if (!to_ring) {
+                    if (is_new) {
+                        uint64_t* e = &s_deque[(size_t)((base + my) & cap_mask) * EW];
+#pragma unroll
+                        for (int i = 0; i < KW; ++i) e[i] = cw[i];
+                        if constexpr (L::HAS_BAL) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                e[KW + i] = (uint64_t)(uint32_t)cbal[2 * i] | ((uint64_t)(uint32_t)cbal[2 * i + 1] << 32);
+                        }
+                    }
+                    n_new_local += n;
+                } else {
+                    unsigned long long rbase = 0;
+                    if (lane == 0) {
+                        atomicAdd(&ctrl->created, (unsigned long long)n);  // counted before it becomes visible
+                        __threadfence();
+                        rbase = atomicAdd(&ctrl->tail, (unsigned long long)n);
+                    }
+                    rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                    if (is_new) {
+                        uint64_t* dst = p.ring + ((rbase + my) & p.ring_mask) * EW;
+#pragma unroll
+                        for (int i = 1; i < KW; ++i) dst[i] = cw[i];
+                        if constexpr (L::HAS_BAL) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                dst[KW + i] = (uint64_t)(uint32_t)cbal[2 * i] | ((uint64_t)(uint32_t)cbal[2 * i + 1] << 32);
+                        }
+                        __threadfence();
+                        *(volatile uint64_t*)dst = cw[0];
+                    }
+                }
+                n_new_total += n;
             };
 
             // -- candidates: ops in the open slots
@@ -469,7 +554,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 int32_t cbal[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                bool ok = cand && model_step<MODEL>(op, creg, cbal, p.read_bal, neg_ok != 0);
+                bool ok = cand && model_step<MODEL>(op, creg, cbal, p.read_bal, neg_ok != 0, gj, w[1], p.set_need);
                 const bool is_front = t == rslot;
                 uint64_t cw[KW];
 #pragma unroll
@@ -503,7 +588,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 }
                 if (ok && !is_front) cw[1] |= 1ull << t;
                 cw[0] = KEY_VALID | ((uint64_t)(uint32_t)cgj << 32) |
-                        ((MODEL == JTB_MODEL_BANK) ? 0ull : (uint64_t)(uint32_t)creg);
+                        ((MODEL == JTB_MODEL_BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
                 int is_new = 0;
                 if (ok) {
                     if (cgj >= gj_end) {
@@ -558,11 +643,11 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 int32_t cbal[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                const bool ok = cand && model_step<MODEL>(cop, creg, cbal, p.read_bal, neg_ok != 0);
+                const bool ok = cand && model_step<MODEL>(cop, creg, cbal, p.read_bal, neg_ok != 0, gj, w[1], p.set_need);
 #pragma unroll
                 for (int i = 1; i < KW; ++i) if (i == cr.word) cw[i] += 1ull << shift;
                 cw[0] = KEY_VALID | ((uint64_t)(uint32_t)gj << 32) |
-                        ((MODEL == JTB_MODEL_BANK) ? 0ull : (uint64_t)(uint32_t)creg);
+                        ((MODEL == JTB_MODEL_BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
                 int is_new = 0;
                 if (ok) {
                     int plen;
@@ -578,7 +663,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 push_children(is_new != 0, cw, cbal);
             }
             if (lane == 0) {
-                if (n_new_total) atomicAdd(&sh.n_new, (unsigned)n_new_total);
+                if (n_new_local) atomicAdd(&sh.n_new, (unsigned)n_new_local);
                 my_expansions++;
                 my_configs += n_new_total;
                 if (++my_steps >= 32 || my_configs >= 512) {

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
-           "jtb_table_bench", "jtb_get_stats"]
+           "jtb_table_bench", "jtb_get_stats", "jtb_struct_size"]
 
 _lib = None
 _lock = threading.Lock()
@@ -56,6 +56,7 @@ def lib() -> C.CDLL:
                                   "g.build()'` (there is no CPU fallback)")
             L = C.CDLL(LIB_PATH)
             L.jtb_abi_version.restype = C.c_int
+            L.jtb_struct_size.restype = C.c_long
             L.jtb_device_count.restype = C.c_int
             L.jtb_create.restype = C.c_void_p
             L.jtb_create.argtypes = [C.c_void_p]
@@ -123,29 +124,11 @@ class Context:
     def check_set_full(self, h: FlatHistory, linearizable: bool = True) -> dict:
         ch = as_c_history(h)
         shards = (abi.CSetFullShard * h.n_shards)()
-        cap = int(np.count_nonzero((h.f == 3) & (h.type == 0))) + 1
-        elem_off = np.zeros(h.n_shards + 1, np.int64)
-        elem_id = np.zeros(cap, np.int32)
-        elem_outcome = np.zeros(cap, np.uint8)
-        elem_lat = np.zeros(cap, np.int64)
-        elem_dup = np.zeros(cap, np.int32)
-        out = abi.CSetFullOut(C.cast(shards, C.c_void_p), cap, elem_off.ctypes.data,
-                              elem_id.ctypes.data, elem_outcome.ctypes.data, elem_lat.ctypes.data,
-                              elem_dup.ctypes.data)
+        out, bufs = abi.alloc_setfull_out(h, shards)
         rc = lib().jtb_check_set_full(self._h, C.addressof(ch), int(linearizable), C.addressof(out))
         if rc != 0:
             raise NativeError(f"jtb_check_set_full rc={rc}: {self._err()}")
-        n = int(elem_off[-1])
-        fields = ("valid", "attempt_count", "stable_count", "lost_count", "never_read_count",
-                  "stale_count", "duplicated_count", "stable_latency_max_ms", "lost_latency_max_ms")
-        return {
-            "valid": out.valid, "n_failures": out.n_failures, "seconds": out.seconds_total,
-            "seconds_kernel": out.seconds_kernel,
-            "shards": [{f: getattr(s, f) for f in fields} for s in shards],
-            "elem_off": elem_off.copy(), "elem_id": elem_id[:n].copy(),
-            "elem_outcome": elem_outcome[:n].copy(), "elem_latency_ms": elem_lat[:n].copy(),
-            "elem_dup_count": elem_dup[:n].copy(),
-        }
+        return abi.setfull_to_dict(out, shards, bufs)
 
     # ---- hot path A8 ----------------------------------------------------------------------------
     def check_bank_totals(self, h: FlatHistory, model: CModel, total_amount: int = 0) -> dict:

@@ -56,32 +56,11 @@ def check_linearizable(h: FlatHistory, model: CModel, algo: int = ALGO_WGL_COMPA
 def check_set_full(h: FlatHistory, linearizable: bool = True) -> dict:
     ch = as_c_history(h)
     shards = (abi.CSetFullShard * h.n_shards)()
-    cap = int(np.count_nonzero((h.f == 3) & (h.type == 0))) + 1
-    elem_off = np.zeros(h.n_shards + 1, np.int64)
-    elem_id = np.zeros(cap, np.int32)
-    elem_outcome = np.zeros(cap, np.uint8)
-    elem_lat = np.zeros(cap, np.int64)
-    elem_dup = np.zeros(cap, np.int32)
-    out = abi.CSetFullOut(C.cast(shards, C.c_void_p), cap, elem_off.ctypes.data, elem_id.ctypes.data,
-                          elem_outcome.ctypes.data, elem_lat.ctypes.data, elem_dup.ctypes.data)
+    out, bufs = abi.alloc_setfull_out(h, shards)
     rc = lib().jtbo_check_set_full(C.byref(ch), int(linearizable), C.byref(out))
     if rc != 0:
         raise RuntimeError(lib().jtbo_scan_last_error().decode())
-    return abi_setfull_to_dict(out, shards, elem_off, elem_id, elem_outcome, elem_lat, elem_dup)
-
-
-def abi_setfull_to_dict(out, shards, elem_off, elem_id, elem_outcome, elem_lat, elem_dup) -> dict:
-    n = int(elem_off[-1])
-    fields = ("valid", "attempt_count", "stable_count", "lost_count", "never_read_count",
-              "stale_count", "duplicated_count", "stable_latency_max_ms", "lost_latency_max_ms")
-    return {
-        "valid": out.valid, "n_failures": out.n_failures, "seconds": out.seconds_total,
-        "seconds_kernel": out.seconds_kernel,
-        "shards": [{f: getattr(s, f) for f in fields} for s in shards],
-        "elem_off": elem_off.copy(), "elem_id": elem_id[:n].copy(),
-        "elem_outcome": elem_outcome[:n].copy(), "elem_latency_ms": elem_lat[:n].copy(),
-        "elem_dup_count": elem_dup[:n].copy(),
-    }
+    return abi.setfull_to_dict(out, shards, bufs)
 
 
 def check_bank_totals(h: FlatHistory, model: CModel, total_amount: int = 0) -> dict:

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <map>
+#include <set>
 #include <unordered_map>
 
 #include "oracle_common.h"
@@ -147,6 +148,42 @@ int jtbo_check_set_full(const jtb_history* h, int linearizable, jtb_setfull_out*
             out->valid = std::max(out->valid, valid);
             out->n_failures += valid != JTB_VALID;
             if (out->elem_capacity > 0) out->elem_off[s + 1] = elem_cursor;
+        }
+        // ---- (read-all-invoked-adds), workloads/set_full.clj:51-75, literally: -------------------
+        //   all-invoked-adds = set of :value over ops with :f :add and :type :invoke
+        //   final-reads      = ops with :f :read, :type :ok, :final? true
+        //   suspect          = final reads whose value does not contain every invoked add
+        out->n_suspect = 0;
+        out->raia_valid = JTB_VALID;
+        int64_t missing_cursor = 0;
+        if (out->suspect_capacity > 0) out->suspect_missing_off[0] = 0;
+        for (int s = 0; s < h->n_shards; ++s) {
+            std::set<int32_t> all_invoked_adds;
+            for (int64_t e = h->shard_off[s]; e < h->shard_off[s + 1]; ++e)
+                if (h->process[e] >= 0 && h->f[e] == JTB_F_ADD && h->type[e] == JTB_T_INVOKE) all_invoked_adds.insert(h->a[e]);
+            int n_suspect_shard = 0;
+            for (int64_t e = h->shard_off[s]; e < h->shard_off[s + 1]; ++e) {
+                if (h->process[e] < 0 || h->f[e] != JTB_F_READ || h->type[e] != JTB_T_OK) continue;
+                if (!h->flags || !(h->flags[e] & JTB_FLAG_FINAL)) continue;
+                const int32_t* pl = h->payload + h->payload_off[e];
+                std::set<int32_t> value(pl, pl + std::max(0, (int)h->payload_len[e]));
+                std::vector<int32_t> missing;
+                for (int32_t v : all_invoked_adds)
+                    if (!value.count(v)) missing.push_back(v);
+                if (missing.empty()) continue;
+                ++n_suspect_shard;
+                if (out->suspect_capacity > 0) {
+                    if (out->n_suspect >= out->suspect_capacity || missing_cursor + (int64_t)missing.size() > out->missing_capacity)
+                        throw std::runtime_error("suspect/missing capacity too small");
+                    out->suspect_shard[out->n_suspect] = s;
+                    out->suspect_index[out->n_suspect] = h->index[e];
+                    for (int32_t v : missing) out->missing_ids[missing_cursor++] = v;
+                    out->suspect_missing_off[out->n_suspect + 1] = missing_cursor;
+                }
+                out->n_suspect++;
+            }
+            out->shards[s].suspect_final_reads = n_suspect_shard;
+            if (n_suspect_shard) out->raia_valid = JTB_INVALID;
         }
         out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         out->seconds_kernel = out->seconds_total;

@@ -39,16 +39,13 @@ def test_no_cpu_fallback_without_device():
         native.Context(device=0)
 
 
-def test_struct_sizes_match_header():
-    # sizes computed from the C declarations (LP64, natural alignment)
-    assert ctypes.sizeof(history.CHistory) == 8 + 12 * 8 + 8 + 8 + 2 * 8  # n_events, 12 ptrs, n_payload, n_shards(+pad), 2 ptrs
-    assert ctypes.sizeof(history.CModel) == 4 * 3 + 4 * 8 + 4 * 8 + 4
-    assert ctypes.sizeof(abi.COpts) == 32
-    assert ctypes.sizeof(abi.CLinShard) == 32
-    assert ctypes.sizeof(abi.CLinResult) == 56
-    assert ctypes.sizeof(abi.CSetFullShard) == 48
-    assert ctypes.sizeof(abi.CSetFullOut) == 8 * 7 + 8 + 16
-    assert ctypes.sizeof(abi.CBankResult) == 8 + 16 + 8 + 40 + 60 + 4 + 16 + 8 + 16
+def test_struct_sizes_match_the_compiled_library():
+    lib = native.lib()
+    images = [history.CHistory, history.CModel, abi.COpts, abi.CLinShard, abi.CLinResult, abi.CSetFullShard,
+              abi.CSetFullOut, abi.CBankResult]
+    for which, img in enumerate(images):
+        assert lib.jtb_struct_size(which) == ctypes.sizeof(img), img.__name__
+    assert lib.jtb_struct_size(99) == -1
 
 
 def test_product_does_not_import_the_oracle():

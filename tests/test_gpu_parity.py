@@ -29,7 +29,7 @@ def same_verdict(g, o):
         assert gs["previous_ok_index"] == os_["previous_ok_index"], (gs, os_)
 
 
-GPU_LIN_KATS = [k for k in kat.ALL_LIN_KATS if k[1] != "set"]
+GPU_LIN_KATS = list(kat.ALL_LIN_KATS)
 
 
 @pytest.mark.parametrize("name,model,text,expect,witness", GPU_LIN_KATS, ids=[k[0] for k in GPU_LIN_KATS])
@@ -48,7 +48,7 @@ def test_bank_negative_balances_forbidden(gpu_ctx):
     assert gpu_ctx.check_linearizable(h, model_for("bank"))["valid"] == H.VALID
 
 
-@pytest.mark.parametrize("model", ["register", "cas-register", "bank"])
+@pytest.mark.parametrize("model", ["register", "cas-register", "bank", "set"])
 def test_random_small(gpu_ctx, oracle_mod, model):
     for seed in range(40):
         spec = synth.SynthSpec(model, n_ops=60, n_clients=4, seed=seed, p_info=0.1 if seed % 2 else 0.0,
@@ -114,6 +114,19 @@ def test_multi_shard(gpu_ctx, oracle_mod):
     assert g["n_failures"] == o["n_failures"]
 
 
+def test_set_model_keyed_c4_lite(gpu_ctx, oracle_mod):
+    """BASELINE config #4 shape (set-full workload, many ledgers) under the knossos set model."""
+    for seed, stale in ((1, False), (2, True)):
+        h = synth.generate(synth.SynthSpec("set", 6000, 32, seed, p_info=0.01, n_keys=8, stale_read=stale,
+                                           tau_think_ns=5e6))
+        m = model_for("set")
+        g = gpu_ctx.check_linearizable(h, m)
+        o = oracle_mod.check_linearizable(h, m, 3, n_threads=4)
+        same_verdict(g, o)
+        if stale:
+            assert o["valid"] == H.INVALID
+
+
 def test_budget_gives_unknown(oracle_mod):
     from jepsen_tigerbeetle_b200 import native
     h = synth.generate(synth.SynthSpec("bank", 10000, 32, 1, tau_think_ns=20e6, stale_read=True))
@@ -126,6 +139,7 @@ def test_budget_gives_unknown(oracle_mod):
 def sf_equal(g, o):
     assert g["valid"] == o["valid"]
     assert g["shards"] == o["shards"]
+    assert g["raia_valid"] == o["raia_valid"] and g["suspect_final_reads"] == o["suspect_final_reads"]
     for k in ("elem_off", "elem_id", "elem_outcome", "elem_latency_ms", "elem_dup_count"):
         assert np.array_equal(g[k], o[k]), k
 
@@ -160,3 +174,37 @@ def test_bank_totals(gpu_ctx, oracle_mod):
         for k in g:
             if not k.startswith("seconds"):
                 assert g[k] == o[k], (k, neg_ok)
+
+
+def test_read_all_invoked_adds(gpu_ctx, oracle_mod):
+    """workloads/set_full.clj:51-75 on the device: final reads that miss invoked adds."""
+    h = synth.config_c4(seed=3, n_keys=4, n_ops=4000)
+    sf_equal(gpu_ctx.check_set_full(h), oracle_mod.check_set_full(h))
+    finals = np.flatnonzero(((h.flags & 1) != 0) & (h.type == 1))
+    for e in finals[:2]:
+        h.payload_len[e] -= 3          # the final read of two ledgers loses its last three elements
+    g, o = gpu_ctx.check_set_full(h), oracle_mod.check_set_full(h)
+    sf_equal(g, o)
+    assert g["raia_valid"] == H.INVALID and len(g["suspect_final_reads"]) == 2
+    assert all(len(s["missing"]) == 3 for s in g["suspect_final_reads"])
+
+
+def test_checker_protocol_end_to_end(gpu_ctx):
+    """The reference's compose maps, through the Python mirror of the Checker protocol."""
+    from jepsen_tigerbeetle_b200 import checker as ck
+    h = synth.config_c4(seed=4, n_keys=3, n_ops=1500)
+    c = ck.independent_checker(ck.compose({"set-full": ck.set_full({"linearizable?": True}, ctx=gpu_ctx),
+                                           "read-all-invoked-adds": ck.read_all_invoked_adds(ctx=gpu_ctx),
+                                           "linear": ck.linearizable({"model": "set"}, ctx=gpu_ctx)}))
+    r = ck.check_safe(c, {}, h)
+    assert set(r["results"]) == {1, 2, 3}
+    for k, m in r["results"].items():
+        assert set(m) == {"set-full", "read-all-invoked-adds", "linear", "valid?"}
+        assert m["linear"]["valid?"] is True and m["read-all-invoked-adds"]["valid?"] is True
+    hb = synth.generate(synth.SynthSpec("bank", 800, 8, 2, tau_think_ns=10e6, stale_read=True))
+    cb = ck.compose({"SI": ck.bank_checker({"negative-balances?": True}, ctx=gpu_ctx),
+                     "linear": ck.linearizable({"model": "bank"}, ctx=gpu_ctx)})
+    rb = ck.check_safe(cb, {"accounts": list(range(1, 9)), "total-amount": 0}, hb)
+    assert rb["SI"]["valid?"] is True          # totals are preserved by a stale read ...
+    assert rb["linear"]["valid?"] is False     # ... but the history is not linearizable (SURVEY B42)
+    assert rb["valid?"] is False and rb["linear"]["op"]["index"] >= 0
