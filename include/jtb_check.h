@@ -238,6 +238,10 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
  * out[12..14] = host->device bytes, device->host bytes, CUDA kernels launched */
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n);
 
+/* ---- diagnostics: host preparation only (pairing, slots, tables) — no device work; returns seconds
+ * or a negative value on malformed input.  Lets callers see the host share of time-to-verdict. */
+double jtb_prepare_seconds(const jtb_history* h, const jtb_model* m);
+
 /* ---- K2 in isolation: visited-table probe/insert microbenchmark (roofline evidence) ----------- *
  * Inserts n_keys pseudo-random 128-bit keys then probes them `rounds` times; returns device
  * seconds for insert and probe phases.  variant selects the probe path.          */

@@ -395,6 +395,13 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
     return run_bank_totals(ctx->stream, ctx->ev0, ctx->ev1, h, accounts, total_amount, out, ctx->err);
 }
 
+double jtb_prepare_seconds(const jtb_history* h, const jtb_model* m) {
+    const double t0 = now_s();
+    Prepared P;
+    if (!prepare(h, m, P)) return -1.0;
+    return now_s() - t0;
+}
+
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n) {
     if (!ctx) return -1;
     for (int i = 0; i < n && i < 16; ++i) out[i] = ctx->stats[i];

@@ -103,19 +103,53 @@ OpRec resolve(const jtb_history* h, const jtb_model* m, int64_t ev, Prepared& ou
 bool build_set_tables(const jtb_history* h, ShardTmp& t, const std::vector<int32_t>& gid, int64_t rank_base,
                       const std::vector<std::pair<int, int>>& field, const std::vector<int32_t>& fr_pos,
                       Prepared& out) {
-    struct Add { int op; int32_t elem; bool crashed; int inv_pos, ret_pos, rank, slot, cls; };
-    std::vector<Add> adds;
-    for (int i = 0; i < (int)t.ops.size(); ++i) {
-        const HOp& o = t.ops[i];
-        const int64_t ev = o.crashed ? o.inv_ev : o.ret_ev;
-        if (h->f[ev] != JTB_F_ADD) continue;
-        adds.push_back(Add{i, h->a[ev], o.crashed, o.inv_pos, o.ret_pos, o.rank, o.slot, o.cls});
-    }
+    struct Add { int32_t elem; bool crashed; int inv_pos, ret_pos, rank, slot, cls; };
     for (auto& f : field)
         if (f.first != 1) return false;
     for (auto& mem : t.cls_members)
         if (mem.size() > 1) return false;  // the same element crashed twice: multi-provider
+    // adds per slot (completed, non-overlapping, in invocation order) and crashed adds in invocation order
+    std::vector<std::vector<Add>> by_slot(64);
+    std::vector<Add> crashed;
+    std::vector<int> add_ret_sorted;       // ret_pos of completed adds, ascending
+    std::vector<int32_t> elems;            // sorted unique element values of all adds
+    for (int i = 0; i < (int)t.ops.size(); ++i) {
+        const HOp& o = t.ops[i];
+        const int64_t ev = o.crashed ? o.inv_ev : o.ret_ev;
+        if (h->f[ev] != JTB_F_ADD) continue;
+        Add a{h->a[ev], o.crashed, o.inv_pos, o.ret_pos, o.rank, o.slot, o.cls};
+        elems.push_back(a.elem);
+        if (o.crashed) crashed.push_back(a);
+        else { by_slot[o.slot].push_back(a); add_ret_sorted.push_back(o.ret_pos); }
+    }
+    std::sort(add_ret_sorted.begin(), add_ret_sorted.end());
+    std::sort(elems.begin(), elems.end());
+    elems.erase(std::unique(elems.begin(), elems.end()), elems.end());
+    // element value -> dense id: direct-address table when the value range is reasonably dense
+    std::vector<int32_t> direct;
+    const int64_t lo_e = elems.empty() ? 0 : elems.front(), hi_e = elems.empty() ? -1 : elems.back();
+    if (!elems.empty() && hi_e - lo_e + 1 <= (int64_t)elems.size() * 256 + 4096) {
+        direct.assign((size_t)(hi_e - lo_e + 1), -1);
+        for (size_t k = 0; k < elems.size(); ++k) direct[(size_t)(elems[k] - lo_e)] = (int32_t)k;
+    }
+    auto elem_id = [&](int32_t e) -> int {
+        if (!direct.empty()) return (e < lo_e || e > hi_e) ? -1 : direct[(size_t)(e - lo_e)];
+        auto it = std::lower_bound(elems.begin(), elems.end(), e);
+        return (it != elems.end() && *it == e) ? (int)(it - elems.begin()) : -1;
+    };
+    // per element: earliest return among its completed adds, and how many completed adds carry it
+    std::vector<int> first_ret(elems.size(), INT_MAX), n_completed(elems.size(), 0);
+    for (auto& v : by_slot)
+        for (const Add& a : v) {
+            const int id = elem_id(a.elem);
+            first_ret[id] = std::min(first_ret[id], a.ret_pos);
+            n_completed[id]++;
+        }
+    bool dup_completed = false;
+    for (int c : n_completed) dup_completed |= c > 1;
     const int R = (int)t.rets.size();
+    std::vector<int32_t> V;
+    std::vector<const Add*> overlap;
     for (int j = 0; j < R; ++j) {
         const int i = t.rets[j];
         const HOp& ro = t.ops[i];
@@ -124,55 +158,77 @@ bool build_set_tables(const jtb_history* h, ShardTmp& t, const std::vector<int32
         const int n = h->payload_len[ro.ret_ev];
         if (n < 0) { rec.x |= OP_IMPOSSIBLE; continue; }
         const int32_t* pl = h->payload + h->payload_off[ro.ret_ev];
-        std::vector<int32_t> V(pl, pl + n);
-        std::sort(V.begin(), V.end());
+        V.assign(pl, pl + n);
+        if (!std::is_sorted(V.begin(), V.end())) std::sort(V.begin(), V.end());
         V.erase(std::unique(V.begin(), V.end()), V.end());
         auto inV = [&](int32_t e) { return std::binary_search(V.begin(), V.end(), e); };
+        // overlapping adds: per slot the run of ops with ret_pos > inv(rho) and inv_pos < ret(rho)
+        overlap.clear();
+        for (auto& v : by_slot) {
+            auto it = std::partition_point(v.begin(), v.end(), [&](const Add& a) { return a.ret_pos < ro.inv_pos; });
+            for (; it != v.end() && it->inv_pos < ro.ret_pos; ++it) overlap.push_back(&*it);
+        }
+        for (const Add& a : crashed) {
+            if (a.inv_pos >= ro.ret_pos) break;
+            overlap.push_back(&a);
+        }
+        // adds that returned before rho was invoked are always linearized: all of them must be in V
+        const int n_before = (int)(std::lower_bound(add_ret_sorted.begin(), add_ret_sorted.end(), ro.inv_pos) -
+                                   add_ret_sorted.begin());
         bool impossible = false;
-        std::vector<int32_t> covered;  // elements of V provided by adds that returned before rho's invoke
-        std::vector<const Add*> overlap;
-        for (const Add& x : adds) {
-            if (x.inv_pos >= ro.ret_pos) continue;                 // invoked after rho returned
-            if (!x.crashed && x.ret_pos < ro.inv_pos) {            // returned before rho was invoked
-                if (!inV(x.elem)) { impossible = true; break; }
-                covered.push_back(x.elem);
-            } else overlap.push_back(&x);
+        int before_in_V = 0;
+        for (int32_t e : V) {
+            const int id = elem_id(e);
+            if (id < 0) { impossible = true; break; }        // nobody ever added it
+            if (first_ret[id] < ro.inv_pos) {                 // covered by an add that already returned
+                if (!dup_completed) before_in_V += 1;
+                continue;
+            }
+            int providers = 0;
+            for (const Add* x : overlap) providers += x->elem == e;
+            if (providers == 0) { impossible = true; break; }
+            if (providers > 1) return false;
         }
         if (!impossible) {
-            std::sort(covered.begin(), covered.end());
-            // every element of V needs a provider; exactly one overlapping provider if not covered
-            for (int32_t e : V) {
-                if (std::binary_search(covered.begin(), covered.end(), e)) continue;
-                int providers = 0;
-                for (const Add* x : overlap) providers += x->elem == e;
-                if (providers == 0) { impossible = true; break; }
-                if (providers > 1) return false;
+            if (dup_completed) {  // rare: count every before-add whose element is in V
+                before_in_V = 0;
+                for (auto& v : by_slot)
+                    for (const Add& a : v)
+                        if (a.ret_pos < ro.inv_pos && inV(a.elem)) ++before_in_V;
             }
+            if (before_in_V != n_before) impossible = true;   // a returned add is missing from the read
         }
         if (impossible) { rec.x |= OP_IMPOSSIBLE; continue; }
         // first frontier rank at which rho is open: smallest g with fr_pos[g] > inv_pos(rho)
-        int g0 = (int)(std::upper_bound(fr_pos.begin(), fr_pos.end(), ro.inv_pos) - fr_pos.begin());
+        const int g0 = (int)(std::upper_bound(fr_pos.begin(), fr_pos.end(), ro.inv_pos) - fr_pos.begin());
         rec.y = (int32_t)(out.set_need.size() / 2);
         rec.z = (int32_t)(rank_base + g0);
         rec.w = (int32_t)(rank_base + j);
+        // classify the overlapping adds once
+        struct Ov { const Add* x; bool want; };
+        std::vector<Ov> ov;
+        for (const Add* x : overlap) {
+            const int id = elem_id(x->elem);
+            const bool want = inV(x->elem);
+            if (want && first_ret[id] < ro.inv_pos) continue;   // element already provided: unconstrained
+            ov.push_back(Ov{x, want});
+        }
         for (int g = g0; g <= j; ++g) {
             uint64_t need = 0, care = 0;
             bool feasible = true;
-            for (const Add* x : overlap) {
-                const bool covered_e = std::binary_search(covered.begin(), covered.end(), x->elem);
-                const bool want = inV(x->elem);
-                if (want && covered_e) continue;                    // unconstrained
+            for (const Ov& o2 : ov) {
+                const Add* x = o2.x;
                 if (x->crashed) {
                     const uint64_t bit = 1ull << (field[x->cls].second & 0xff);
-                    if (x->inv_pos < fr_pos[g]) { care |= bit; if (want) need |= bit; }
-                    else if (want) feasible = false;
+                    if (x->inv_pos < fr_pos[g]) { care |= bit; if (o2.want) need |= bit; }
+                    else if (o2.want) feasible = false;
                 } else if (x->rank < g) {
-                    if (!want) feasible = false;                    // already linearized but not in V
+                    if (!o2.want) feasible = false;                 // already linearized but not in V
                 } else if (x->inv_pos < fr_pos[g]) {
                     const uint64_t bit = 1ull << x->slot;
                     care |= bit;
-                    if (want) need |= bit;
-                } else if (want) feasible = false;                  // required but not invoked yet
+                    if (o2.want) need |= bit;
+                } else if (o2.want) feasible = false;               // required but not invoked yet
             }
             if (!feasible) { need = ~0ull; care = 0; }              // (w & 0) == ~0 never holds
             out.set_need.push_back(need);

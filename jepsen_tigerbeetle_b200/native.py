@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
-           "jtb_table_bench", "jtb_get_stats", "jtb_struct_size"]
+           "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds"]
 
 _lib = None
 _lock = threading.Lock()
@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
             L = C.CDLL(LIB_PATH)
             L.jtb_abi_version.restype = C.c_int
             L.jtb_struct_size.restype = C.c_long
+            L.jtb_prepare_seconds.restype = C.c_double
+            L.jtb_prepare_seconds.argtypes = [C.c_void_p, C.c_void_p]
             L.jtb_device_count.restype = C.c_int
             L.jtb_create.restype = C.c_void_p
             L.jtb_create.argtypes = [C.c_void_p]
@@ -167,6 +169,12 @@ class Context:
             raise NativeError(f"jtb_table_bench rc={rc}: {self._err()}")
         return {"insert_seconds": ins.value, "probe_seconds": prb.value, "found": found.value,
                 "n_keys": n_keys, "rounds": rounds, "variant": variant}
+
+
+def prepare_seconds(h: FlatHistory, model: CModel) -> float:
+    """Host preparation time only (no GPU needed)."""
+    ch = as_c_history(h)
+    return lib().jtb_prepare_seconds(C.addressof(ch), C.addressof(model))
 
 
 def device_count() -> int:

@@ -181,18 +181,21 @@ def test_read_all_invoked_adds(gpu_ctx, oracle_mod):
     h = synth.config_c4(seed=3, n_keys=4, n_ops=4000)
     sf_equal(gpu_ctx.check_set_full(h), oracle_mod.check_set_full(h))
     finals = np.flatnonzero(((h.flags & 1) != 0) & (h.type == 1))
+    before = {s["index"]: len(s["missing"]) for s in gpu_ctx.check_set_full(h)["suspect_final_reads"]}
     for e in finals[:2]:
         h.payload_len[e] -= 3          # the final read of two ledgers loses its last three elements
     g, o = gpu_ctx.check_set_full(h), oracle_mod.check_set_full(h)
     sf_equal(g, o)
-    assert g["raia_valid"] == H.INVALID and len(g["suspect_final_reads"]) == 2
-    assert all(len(s["missing"]) == 3 for s in g["suspect_final_reads"])
+    after = {s["index"]: len(s["missing"]) for s in g["suspect_final_reads"]}
+    assert g["raia_valid"] == H.INVALID
+    # (never-applied crashed adds are legitimately missing already; the truncation adds exactly three)
+    assert sorted(after[i] - before.get(i, 0) for i in after) == [0, 0, 3, 3]
 
 
 def test_checker_protocol_end_to_end(gpu_ctx):
     """The reference's compose maps, through the Python mirror of the Checker protocol."""
     from jepsen_tigerbeetle_b200 import checker as ck
-    h = synth.config_c4(seed=4, n_keys=3, n_ops=1500)
+    h = synth.config_c4(seed=4, n_keys=3, n_ops=1500, p_info=0.0)
     c = ck.independent_checker(ck.compose({"set-full": ck.set_full({"linearizable?": True}, ctx=gpu_ctx),
                                            "read-all-invoked-adds": ck.read_all_invoked_adds(ctx=gpu_ctx),
                                            "linear": ck.linearizable({"model": "set"}, ctx=gpu_ctx)}))
