@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -209,19 +210,18 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     std::memset(&hc, 0, sizeof hc);
     std::vector<int> h_found(n_shards, 0), h_max(n_shards, 0);
     if (!searchable.empty()) {
-        if (upload(ctx, ctx->rows, P.rows) || upload(ctx, ctx->ops, P.ops) || upload(ctx, ctx->read_bal, P.read_bal) || upload(ctx, ctx->set_need, P.set_need) ||
-            upload(ctx, ctx->classes, P.classes) || upload(ctx, ctx->cls_inv, P.cls_inv_pos))
+        if (upload(ctx, ctx->rows, P.rows) || upload(ctx, ctx->classes, P.classes) || upload(ctx, ctx->cls_inv, P.cls_inv_pos))
             return -1;
         if (ensure(ctx, ctx->ctrl, sizeof(Ctrl)) || ensure(ctx, ctx->found, n_shards * sizeof(int)) ||
             ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
             return -1;
         // CTA deque / grid
         const int cand_rounds = P.S_pad / 32, cls_rounds = (P.max_nc + 31) / 32;
-        const uint32_t worst_push = WGL_WARPS * WGL_G * 32 * (cand_rounds + cls_rounds);
+        const uint32_t worst_push = WGL_BATCH * 32 * (cand_rounds + cls_rounds);   // per CTA step (overflow -> ring)
         uint32_t deque_cap = 1024;                       // fixed: a full deque overflows to the ring
         while ((size_t)deque_cap * EW * 8 > 48 * 1024) deque_cap >>= 1;
         const uint32_t stage_cap = std::max(deque_cap, worst_push);
-        const size_t smem = (size_t)deque_cap * EW * 8;
+        const size_t smem = (size_t)(deque_cap + WGL_BATCH) * EW * 8;   // deque + staged batch
         int ctas_per_sm = (int)std::min<size_t>(4, (220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, ctas_per_sm);
         const int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;
@@ -260,9 +260,6 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             ++attempts;
             WglParams p{};
             p.rows = (const int32_t*)ctx->rows.p;
-            p.ops = (const int4*)ctx->ops.p;
-            p.read_bal = (const int32_t*)ctx->read_bal.p;
-            p.set_need = (const uint64_t*)ctx->set_need.p;
             p.classes = (const ClassRec*)ctx->classes.p;
             p.cls_inv_pos = (const int32_t*)ctx->cls_inv.p;
             p.table = (uint64_t*)ctx->table.p;
@@ -273,7 +270,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.ctrl = (Ctrl*)ctx->ctrl.p;
             p.shard_found = (int*)ctx->found.p;
             p.shard_max_rank = (int*)ctx->maxrank.p;
-            p.row_words = P.S_pad + ROW_EXTRA;
+            p.row_words = P.row_words;
             p.S_pad = P.S_pad;
             p.n_shards = n_shards;
             p.max_nc = P.max_nc;
@@ -286,6 +283,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             }
             p.time_budget_ns = (unsigned long long)ctx->opts.time_budget_ms * 1000000ull;
             p.deque_cap = deque_cap;
+            p.cas_first = getenv("JTB_CAS_FIRST") ? atoi(getenv("JTB_CAS_FIRST")) : 0;
             int rc;
             if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem);
             else if (m->kind == JTB_MODEL_SET) rc = launch_wgl<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem);

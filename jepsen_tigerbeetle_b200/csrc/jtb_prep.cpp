@@ -103,6 +103,11 @@ OpRec resolve(const jtb_history* h, const jtb_model* m, int64_t ev, Prepared& ou
 bool build_set_tables(const jtb_history* h, ShardTmp& t, const std::vector<int32_t>& gid, int64_t rank_base,
                       const std::vector<std::pair<int, int>>& field, const std::vector<int32_t>& fr_pos,
                       Prepared& out) {
+    const int RW = out.row_words, SW = slot_words(JTB_MODEL_SET);
+    // mark the inline record of op `gid_` impossible in every row it appears in: ranks [g0, j]
+    auto mark_impossible = [&](int slot, int g0, int j) {
+        for (int g = g0; g <= j; ++g) out.rows[(size_t)(rank_base + g) * RW + ROW_EXTRA + slot * SW] |= OP_IMPOSSIBLE;
+    };
     struct Add { int32_t elem; bool crashed; int inv_pos, ret_pos, rank, slot, cls; };
     for (auto& f : field)
         if (f.first != 1) return false;
@@ -155,8 +160,10 @@ bool build_set_tables(const jtb_history* h, ShardTmp& t, const std::vector<int32
         const HOp& ro = t.ops[i];
         if (h->f[ro.ret_ev] != JTB_F_READ) continue;
         OpRec& rec = out.ops[gid[i]];
+        // first frontier rank at which rho is open: smallest g with fr_pos[g] > inv_pos(rho)
+        const int g0 = (int)(std::upper_bound(fr_pos.begin(), fr_pos.end(), ro.inv_pos) - fr_pos.begin());
         const int n = h->payload_len[ro.ret_ev];
-        if (n < 0) { rec.x |= OP_IMPOSSIBLE; continue; }
+        if (n < 0) { rec.x |= OP_IMPOSSIBLE; mark_impossible(ro.slot, g0, j); continue; }
         const int32_t* pl = h->payload + h->payload_off[ro.ret_ev];
         V.assign(pl, pl + n);
         if (!std::is_sorted(V.begin(), V.end())) std::sort(V.begin(), V.end());
@@ -198,12 +205,7 @@ bool build_set_tables(const jtb_history* h, ShardTmp& t, const std::vector<int32
             }
             if (before_in_V != n_before) impossible = true;   // a returned add is missing from the read
         }
-        if (impossible) { rec.x |= OP_IMPOSSIBLE; continue; }
-        // first frontier rank at which rho is open: smallest g with fr_pos[g] > inv_pos(rho)
-        const int g0 = (int)(std::upper_bound(fr_pos.begin(), fr_pos.end(), ro.inv_pos) - fr_pos.begin());
-        rec.y = (int32_t)(out.set_need.size() / 2);
-        rec.z = (int32_t)(rank_base + g0);
-        rec.w = (int32_t)(rank_base + j);
+        if (impossible) { rec.x |= OP_IMPOSSIBLE; mark_impossible(ro.slot, g0, j); continue; }
         // classify the overlapping adds once
         struct Ov { const Add* x; bool want; };
         std::vector<Ov> ov;
@@ -231,8 +233,9 @@ bool build_set_tables(const jtb_history* h, ShardTmp& t, const std::vector<int32
                 } else if (o2.want) feasible = false;               // required but not invoked yet
             }
             if (!feasible) { need = ~0ull; care = 0; }              // (w & 0) == ~0 never holds
-            out.set_need.push_back(need);
-            out.set_need.push_back(care);
+            int32_t* cell = &out.rows[(size_t)(rank_base + g) * RW + ROW_EXTRA + ro.slot * SW + 4];
+            std::memcpy(cell, &need, 8);
+            std::memcpy(cell + 2, &care, 8);
         }
     }
     return true;
@@ -364,12 +367,14 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
     }
     out.key_words = key_words;
     // ---- pass 3: tables -----------------------------------------------------------------------
-    const int RW = out.S_pad + ROW_EXTRA;
+    const int SW = slot_words(m->kind);
+    const int RW = ROW_EXTRA + out.S_pad * SW;
+    out.row_words = RW;
     out.rank_base.assign(n_shards + 1, 0);
     for (int s = 0; s < n_shards; ++s) out.rank_base[s + 1] = out.rank_base[s] + (int64_t)tmp[s].rets.size();
     out.n_ranks = out.rank_base[n_shards];
     if (out.n_ranks >= (1ll << 31) - 64) { out.error = "history too large"; return false; }
-    out.rows.assign((size_t)out.n_ranks * RW, -1);
+    out.rows.assign((size_t)out.n_ranks * RW, 0);
     out.ret_index.assign((size_t)out.n_ranks, -1);
     for (int s = 0; s < n_shards; ++s) {
         ShardTmp& t = tmp[s];
@@ -397,7 +402,7 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
             for (int i : t.cls_members[c]) out.cls_inv_pos.push_back(t.ops[i].inv_pos);
             out.classes.push_back(cr);
         }
-        // rows: sweep invocations and returns in position order
+        // rows: sweep invocations and returns in position order; slot contents are stored INLINE
         std::vector<int32_t> cur(out.S_pad, -1);
         size_t oi = 0;
         for (int j = 0; j < R; ++j) {
@@ -407,18 +412,23 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
                 ++oi;
             }
             int32_t* row = &out.rows[(size_t)(base + j) * RW];
-            std::memcpy(row, cur.data(), out.S_pad * sizeof(int32_t));
-            uint8_t* nxt = reinterpret_cast<uint8_t*>(row + out.S_pad);
+            uint8_t* nxt = reinterpret_cast<uint8_t*>(row);
             for (int k = 0; k < 32; ++k)
                 nxt[k] = (j + 1 + k < R) ? (uint8_t)t.ops[t.rets[j + 1 + k]].slot : (uint8_t)0xFF;
-            row[out.S_pad + 8] = ro.ret_pos;
-            row[out.S_pad + 9] = s;
-            row[out.S_pad + 10] = (int32_t)(base + R);
-            row[out.S_pad + 11] = cls_base;
-            row[out.S_pad + 12] = (int32_t)t.cls_members.size();
-            row[out.S_pad + 13] = ro.slot;
-            row[out.S_pad + 14] = 0;
-            row[out.S_pad + 15] = 0;
+            row[8] = ro.ret_pos;
+            row[9] = s;
+            row[10] = (int32_t)(base + R);
+            row[11] = cls_base;
+            row[12] = (int32_t)t.cls_members.size();
+            row[13] = ro.slot;
+            for (int sl = 0; sl < out.S_pad; ++sl) {
+                int32_t* cell = row + ROW_EXTRA + sl * SW;
+                if (cur[sl] < 0) { cell[0] = OP_EMPTY; continue; }
+                const OpRec& rec = out.ops[cur[sl]];
+                cell[0] = rec.x; cell[1] = rec.y; cell[2] = rec.z; cell[3] = rec.w;
+                if (m->kind == JTB_MODEL_BANK && (rec.x & 0xff) == JTB_F_READ)
+                    std::memcpy(cell + 4, &out.read_bal[(size_t)rec.z * JTB_MAX_ACCOUNTS], 8 * sizeof(int32_t));
+            }
             out.ret_index[base + j] = h->index[ro.ret_ev];
             cur[ro.slot] = -1;  // the op has returned
         }

@@ -18,9 +18,9 @@ namespace jtb {
 //   x = f | flags<<8   (flag bit 8: impossible — can never be linearized)
 //   register/cas: y = value / cas-old, z = cas-new
 //   bank transfer: y = amount, z = debit slot, w = credit slot
-//   bank read:     y = care mask over account slots, z = index into read_bal (8 int32 each)
-//   set add:       y = dense element id
-//   set read:      y = offset into set_need (per (read, frontier) need/care masks), z = first rank, w = last rank
+//   bank read:     y = care mask over account slots (the balances follow inline in the frontier row)
+//   set add:       y = element value
+//   set read:      (need, care) masks follow inline in the frontier row, per rank
 struct OpRec {
     int32_t x, y, z, w;
 };
@@ -37,27 +37,33 @@ struct ClassRec {
 };
 
 // Row of the frontier table: everything a warp needs to expand a config whose first un-linearized
-// return is global rank gj.  int32 words:
-//   [0, S_pad)            global op id occupying each open-op slot at that return event (-1 none)
-//   [S_pad, S_pad+8)      slots (u8) of the next 32 returns gj+1 .. gj+32 (0xFF beyond the shard end)
-//   [S_pad+8]             position of the return event (for crashed-op eligibility)
-//   [S_pad+9]             shard id
-//   [S_pad+10]            global rank one past the shard's last return (success when reached)
-//   [S_pad+11]            first class record of the shard
-//   [S_pad+12]            number of classes of the shard
-//   [S_pad+13]            slot of this rank's own op
-//   [S_pad+14..15]        pad
+// return is global rank gj, in ONE contiguous read.  int32 words:
+//   [0, 8)     slots (u8) of the next 32 returns gj+1 .. gj+32 (0xFF beyond the shard end)
+//   [8]        position of the return event (for crashed-op eligibility)
+//   [9]        shard id
+//   [10]       global rank one past the shard's last return (success when reached)
+//   [11]       first class record of the shard
+//   [12]       number of classes of the shard
+//   [13]       slot of this rank's own op
+//   [14..15]   pad
+//   [16 + t*SW, 16 + (t+1)*SW)   the op occupying open-op slot t at that return event, INLINE:
+//        words 0..3  OpRec (x = -1: slot empty)
+//        bank  (SW = 12): words 4..11 = the 8 balances a read expects (by account slot; op.y = care mask)
+//        set   (SW = 8):  words 4..7  = (need, care) u64 pair of a read AT THIS RANK:
+//                         consistent <=> (key word1 & care) == need
 constexpr int ROW_EXTRA = 16;
+inline int slot_words(int model) { return model == JTB_MODEL_BANK ? 12 : model == JTB_MODEL_SET ? 8 : 4; }
+constexpr int OP_EMPTY = -1;
 
 struct Prepared {
     int S_pad = 32;          // 32 or 64
     int key_words = 2;       // 64-bit words per key: 2, 4 or 8
     int model = 0;
     int64_t n_ranks = 0;     // total completed ops over all searchable shards
-    std::vector<int32_t> rows;        // n_ranks * (S_pad + ROW_EXTRA)
-    std::vector<OpRec> ops;           // global op table
-    std::vector<int32_t> read_bal;    // bank: 8 per read
-    std::vector<uint64_t> set_need;   // set: (need, care) pairs
+    int row_words = 0;                // ROW_EXTRA + S_pad * slot_words(model)
+    std::vector<int32_t> rows;        // n_ranks * row_words
+    std::vector<OpRec> ops;           // global op table (host side only: copied inline into rows)
+    std::vector<int32_t> read_bal;    // bank: 8 per read (host side only)
     std::vector<ClassRec> classes;
     std::vector<int32_t> cls_inv_pos;
     // per shard (host side)

@@ -59,10 +59,7 @@ struct Ctrl {
 constexpr int CAUSE_RING_FULL = 100;  // internal: the host grows the ring and resumes
 
 struct WglParams {
-    const int32_t* rows;
-    const int4* ops;
-    const int32_t* read_bal;
-    const uint64_t* set_need;   // set model: (need, care) pairs per (read, frontier rank)
+    const int32_t* rows;        // frontier rows with the slot ops inline (jtb_prep.h)
     const ClassRec* classes;
     const int32_t* cls_inv_pos;
     uint64_t* table;        // slots of KW 64-bit words
@@ -78,6 +75,7 @@ struct WglParams {
     int budget_cause;                 // JTB_CAUSE_BUDGET or JTB_CAUSE_TABLE_FULL (load guard)
     unsigned long long time_budget_ns;
     uint32_t deque_cap;     // entries in the CTA's shared-memory deque (power of two)
+    int cas_first;          // probe with atom.cas first (experiment switch, env JTB_CAS_FIRST)
 };
 
 constexpr uint64_t KEY_VALID = 1ull << 63;
@@ -141,11 +139,12 @@ __device__ __forceinline__ uint64_t hash_key(const uint64_t (&k)[KW]) {
 // -1 = table exhausted.  *plen gets the number of slots inspected.
 template <int KW>
 __device__ __forceinline__ int table_insert(uint64_t* table, uint64_t slot_mask, const uint64_t (&k)[KW],
-                                            int* plen) {
+                                            int* plen, bool cas_first = false) {
     uint64_t idx = hash_key<KW>(k) & slot_mask;
     for (int i = 0; i < MAX_PROBE; ++i) {
         uint64_t* slot = table + idx * KW;
-        K128 cur = ldcg128(slot);
+        // load-first: hits (the majority) cost one plain load; cas-first: new configs cost one round trip
+        K128 cur = (KW == 2 && cas_first) ? K128{0, 0} : ldcg128(slot);
         if (cur.lo == 0 && cur.hi == 0) {
             K128 mine{KW == 2 ? k[0] : (k[0] | KEY_LOCK), k[1]};
             K128 old = cas128(slot, K128{0, 0}, mine);
@@ -183,10 +182,10 @@ __device__ __forceinline__ int table_insert(uint64_t* table, uint64_t slot_mask,
 // Model step, inlined per lane (knossos.model; bank: SURVEY §8(a) A7 from
 // src/tigerbeetle/tests/ledger.clj:89-152).  `reg` is the register value (word0 low half),
 // `bal` the 8 balances carried in the entry.
+// `cell` points at the op's inline record in the frontier row (OpRec, then the model's read payload).
 template <int MODEL>
 __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t (&bal)[8],
-                                           const int32_t* __restrict__ read_bal, bool neg_ok, int gj,
-                                           uint64_t w1, const uint64_t* __restrict__ set_need) {
+                                           const int32_t* __restrict__ cell, bool neg_ok, uint64_t w1) {
     const int f = op.x & 0xff;
     if (op.x & OP_IMPOSSIBLE) return false;
     if constexpr (MODEL == JTB_MODEL_REGISTER || MODEL == JTB_MODEL_CAS_REGISTER) {
@@ -206,7 +205,7 @@ __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t 
             return ok;
         }
         // read: every account present in the payload must match
-        const int4* rb = reinterpret_cast<const int4*>(read_bal + (size_t)op.z * 8);
+        const int4* rb = reinterpret_cast<const int4*>(cell + 4);
         const int4 lo = __ldg(rb), hi = __ldg(rb + 1);
         const int care = op.y;
         bool ok = true;
@@ -223,7 +222,7 @@ __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t 
         // grow-only set: adds always apply; a read is consistent iff the constrained bits of key word 1
         // (open-slot mask + crashed-add counts) equal the precomputed pattern for this (read, frontier)
         if (f == JTB_F_ADD) return true;
-        const ulonglong2 nc = __ldg(reinterpret_cast<const ulonglong2*>(set_need) + (op.y + (gj - op.z)));
+        const ulonglong2 nc = __ldg(reinterpret_cast<const ulonglong2*>(cell + 4));
         return (w1 & nc.y) == nc.x;
     } else {
         return false;
@@ -240,14 +239,14 @@ struct EntryLayout {
 constexpr int WGL_WARPS = 8;
 constexpr int WGL_THREADS = WGL_WARPS * 32;
 constexpr unsigned WGL_MAX_DONATE = 64;       // per step, when donating to hungry warps
-constexpr int WGL_G = 2;                      // local entries a warp expands per step (amortises the 3 barriers)
+constexpr unsigned WGL_BATCH = 32;            // deque entries popped per CTA step; warps self-schedule over them
 
 struct CtaShared {
     int stop;
     unsigned top, bot;              // local LIFO deque (monotonic indices, masked on use)
     unsigned pop_top, don_bot;      // snapshots for this step's readers
-    unsigned n_local, n_don;
-    unsigned local_mask;            // warps that pop a local entry this step
+    unsigned n_batch, n_don;
+    unsigned batch_next;            // self-scheduling cursor over the staged batch
     unsigned ticket_mask;           // warps that currently hold a ring ticket
     unsigned assign_mask;           // warps that receive a new ticket this step
     unsigned n_exp, n_new;          // expansions / new children of the running step
@@ -264,14 +263,16 @@ template <int MODEL, int KW>
 __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglParams p, const int neg_ok) {
     using L = EntryLayout<MODEL, KW>;
     constexpr int EW = L::EW;
-    extern __shared__ __align__(16) uint64_t s_deque[];  // deque_cap * EW words
+    extern __shared__ __align__(16) uint64_t s_deque[];  // deque_cap * EW words, then WGL_BATCH * EW staging
     __shared__ CtaShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Ctrl* ctrl = p.ctrl;
     const int cand_rounds = p.S_pad / 32;
     const int cls_rounds = (p.max_nc + 31) / 32;
+    constexpr int SW = MODEL == JTB_MODEL_BANK ? 12 : MODEL == JTB_MODEL_SET ? 8 : 4;  // = slot_words(MODEL)
     const unsigned cap_mask = p.deque_cap - 1;
     const unsigned high = p.deque_cap / 2;   // donate the oldest entries beyond this; overflow goes to the ring
+    uint64_t* const s_batch = s_deque + (size_t)p.deque_cap * EW;
 
     if (tid == 0) {
         sh.stop = 0; sh.top = sh.bot = 0;
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                     const unsigned long long cr = ld_volatile(&ctrl->created);
                     if (ex == cr) { atomicCAS(&ctrl->stop, 0, 1); stop = ld_volatile(&ctrl->stop); }
                     else {
+                        stop = ld_volatile(&ctrl->stop);
                         __nanosleep(sh.backoff);
                         if (sh.backoff < 1024) sh.backoff <<= 1;
                     }
@@ -339,31 +341,30 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             // ---- donation: deque nearly full, other warps hungry (tickets waiting), or pausing ---------
             const unsigned long long hunger = h > t ? h - t : 0;
             const unsigned free_warps = ~sh.ticket_mask & ((1u << WGL_WARPS) - 1);
-            const unsigned keep = max(1, __popc(free_warps));  // what this CTA can pop next step
             unsigned n_don = 0;
             if (stop == 2) n_don = size;  // pause: all live work must be in the ring
             else if (size > high) n_don = size - p.deque_cap / 4;
-            else if (hunger && size > keep)
-                n_don = (unsigned)min((unsigned long long)min(size - keep, WGL_MAX_DONATE), hunger);
+            else if (hunger && size > WGL_WARPS)
+                n_don = (unsigned)min((unsigned long long)min(size - WGL_WARPS, WGL_MAX_DONATE), hunger);
             sh.n_don = n_don;
             sh.don_bot = sh.bot;
             if (n_don) {
                 sh.don_base = atomicAdd(&ctrl->tail, (unsigned long long)n_don);
                 sh.bot += n_don;
             }
-            // ---- local pops go to warps that hold no ticket; the remaining ticketless warps take one ----
-            const unsigned n_free = (unsigned)__popc(free_warps);
-            unsigned n_local = stop ? 0 : min(size - n_don, n_free * WGL_G);
-            // the first min(n_local, n_free) free warps pop; warp with rank k among them takes entries
-            // k, k + n_poppers, ... (deepest first)
-            const unsigned n_poppers = min(n_local, n_free);
-            unsigned local_mask = 0, rest = free_warps;
-            for (unsigned k = 0; k < n_poppers; ++k) { const unsigned b = rest & (0u - rest); local_mask |= b; rest ^= b; }
-            sh.local_mask = local_mask;
-            sh.n_local = n_local;
+            // ---- this step's batch: the deepest entries; warps self-schedule over it ----------------------
+            const unsigned n_batch = stop ? 0 : min(size - n_don, WGL_BATCH);
+            sh.n_batch = n_batch;
+            sh.batch_next = 0;
             sh.pop_top = sh.top;
-            sh.top -= n_local;
-            const unsigned need = stop ? 0 : rest;
+            sh.top -= n_batch;
+            // fewer entries than warps: the surplus ticketless warps wait on ring tickets
+            unsigned need = 0;
+            if (!stop && n_batch < WGL_WARPS) {
+                unsigned want = WGL_WARPS - n_batch - (unsigned)__popc(sh.ticket_mask);
+                unsigned rest = free_warps;
+                while ((int)want > 0 && rest) { const unsigned b = rest & (0u - rest); need |= b; rest ^= b; --want; }
+            }
             sh.assign_mask = need;
             if (need) {
                 sh.ticket_base = atomicAdd(&ctrl->head, (unsigned long long)__popc(need));
@@ -385,79 +386,17 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 *(volatile uint64_t*)dst = src[0];
             }
         }
-        // ---- fetch: a local entry, or poll my ring ticket ----------------------------------------------
-        uint64_t w[KW];
-        int32_t pbal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint64_t w2[WGL_G - 1][KW];            // further local entries of this step
-        int32_t pbal2[WGL_G - 1][8];
-        int n_mine = 0;
-        bool ready = false;
+        // ---- stage the batch (deepest first) so that pushes may reuse the deque space -------------------
+        const unsigned n_batch = sh.n_batch;
+        for (unsigned i = tid; i < n_batch * EW; i += WGL_THREADS) {
+            const unsigned e = i / EW, k = i % EW;
+            s_batch[i] = s_deque[(size_t)((sh.pop_top - 1 - e) & cap_mask) * EW + k];
+        }
         if ((sh.assign_mask >> warp) & 1u) {
             ticket = sh.ticket_base + __popc(sh.assign_mask & ((1u << warp) - 1));
             has_ticket = true;
         }
-        if ((sh.local_mask >> warp) & 1u) {
-            const unsigned k0 = __popc(sh.local_mask & ((1u << warp) - 1));
-            const unsigned n_poppers = __popc(sh.local_mask);
-            const unsigned n_local = sh.n_local;
-#pragma unroll
-            for (int g = 0; g < WGL_G; ++g) {
-                const unsigned k = k0 + g * n_poppers;
-                if (k >= n_local) break;
-                const uint64_t* e = &s_deque[(size_t)((sh.pop_top - 1 - k) & cap_mask) * EW];
-                if (g == 0) {
-#pragma unroll
-                    for (int i = 0; i < KW; ++i) w[i] = e[i];
-                    if constexpr (L::HAS_BAL) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint64_t v = e[KW + i];
-                            pbal[2 * i] = (int32_t)(uint32_t)v;
-                            pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < KW; ++i) w2[g - 1][i] = e[i];
-                    if constexpr (L::HAS_BAL) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint64_t v = e[KW + i];
-                            pbal2[g - 1][2 * i] = (int32_t)(uint32_t)v;
-                            pbal2[g - 1][2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
-                        }
-                    }
-                }
-                n_mine = g + 1;
-            }
-            ready = true;
-        } else if (has_ticket && !exiting) {
-            uint64_t* slot = p.ring + (ticket & p.ring_mask) * EW;
-            w[0] = ld_volatile64(slot);
-            ready = w[0] != 0;   // warp-uniform: all lanes load the same address
-            if (ready) {
-                __threadfence();  // acquire: payload words were written before word0
-#pragma unroll
-                for (int i = 1; i < KW; ++i) w[i] = ldcg64(slot + i);
-                if constexpr (L::HAS_BAL) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint64_t v = ldcg64(slot + KW + i);
-                        pbal[2 * i] = (int32_t)(uint32_t)v;
-                        pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    *(volatile uint64_t*)slot = 0;  // slot consumed
-                    atomicAnd(&sh.ticket_mask, ~(1u << warp));
-                }
-                has_ticket = false;
-            } else if (lane == 0 && warp == 0) {
-                sh.polls++;
-            }
-        }
-        __syncthreads();  // (C) popped / donated entries have been read: pushes may reuse the space
+        __syncthreads();  // (C) batch staged, donated entries copied: pushes may reuse the space
         if (exiting) break;
         if (tid == 0) {  // prefetch the control words of the NEXT step behind this step's expansions
             pre_stop = ld_volatile(&ctrl->stop);
@@ -465,20 +404,63 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             pre_tail = ld_volatile(&ctrl->tail);
         }
 
-        if (ready && n_mine == 0) n_mine = 1;  // an entry served by my ring ticket
-        for (int g = 0; g < n_mine; ++g) {
-            if (g > 0) {
+        // ---- self-scheduled expansion: next staged entry, else one poll of my ring ticket ---------------
+        bool polled = false;
+        unsigned n_done = 0;
+        for (;;) {
+            uint64_t w[KW];
+            int32_t pbal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            bool have = false;
+            unsigned idx = 0;
+            if (lane == 0) idx = atomicAdd(&sh.batch_next, 1u);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx < n_batch) {
+                const uint64_t* e = &s_batch[(size_t)idx * EW];
 #pragma unroll
-                for (int i = 0; i < KW; ++i) w[i] = w2[g - 1][i];
+                for (int i = 0; i < KW; ++i) w[i] = e[i];
+                if constexpr (L::HAS_BAL) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) pbal[i] = pbal2[g - 1][i];
+                    for (int i = 0; i < 4; ++i) {
+                        const uint64_t v = e[KW + i];
+                        pbal[2 * i] = (int32_t)(uint32_t)v;
+                        pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+                    }
+                }
+                have = true;
+            } else if (has_ticket && !polled) {
+                polled = true;
+                uint64_t* slot = p.ring + (ticket & p.ring_mask) * EW;
+                w[0] = ld_volatile64(slot);   // warp-uniform: all lanes load the same address
+                if (w[0] != 0) {
+                    __threadfence();  // acquire: payload words were written before word0
+#pragma unroll
+                    for (int i = 1; i < KW; ++i) w[i] = ldcg64(slot + i);
+                    if constexpr (L::HAS_BAL) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t v = ldcg64(slot + KW + i);
+                            pbal[2 * i] = (int32_t)(uint32_t)v;
+                            pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        *(volatile uint64_t*)slot = 0;  // slot consumed
+                        atomicAnd(&sh.ticket_mask, ~(1u << warp));
+                    }
+                    has_ticket = false;
+                    have = true;
+                } else if (lane == 0 && warp == 0) {
+                    sh.polls++;
+                }
             }
-            if (lane == 0) atomicAdd(&sh.n_exp, 1u);
+            if (!have) break;
+            ++n_done;
             // ---------------- expand (warp-synchronous) ---------------------------------------------
             const int gj = (int)((w[0] >> 32) & 0x3fffffffu);
             const int32_t preg = (int32_t)(uint32_t)w[0];
             const int32_t* row = p.rows + (size_t)gj * p.row_words;
-            const int32_t extra = __ldg(row + p.S_pad + (lane & 15));
+            const int32_t extra = __ldg(row + (lane & 15));
             const int fr_pos = __shfl_sync(0xffffffffu, extra, 8);
             const int shard = __shfl_sync(0xffffffffu, extra, 9);
             const int gj_end = __shfl_sync(0xffffffffu, extra, 10);
@@ -546,15 +528,14 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             // -- candidates: ops in the open slots
             for (int r = 0; r < cand_rounds && shard_alive; ++r) {
                 const int t = r * 32 + lane;
-                const int opid = __ldg(row + t);
-                const bool cand = opid >= 0 && !((w[1] >> t) & 1ull);
-                int4 op = make_int4(OP_IMPOSSIBLE, 0, 0, 0);
-                if (cand) op = __ldg(p.ops + opid);
+                const int32_t* cell = row + ROW_EXTRA + t * SW;
+                const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
+                const bool cand = op.x >= 0 && !((w[1] >> t) & 1ull);
                 int32_t creg = preg;
                 int32_t cbal[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                bool ok = cand && model_step<MODEL>(op, creg, cbal, p.read_bal, neg_ok != 0, gj, w[1], p.set_need);
+                bool ok = cand && model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
                 const bool is_front = t == rslot;
                 uint64_t cw[KW];
 #pragma unroll
@@ -582,7 +563,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                         adv += n;
                         if (n < 32) break;
                         rw += (size_t)32 * p.row_words;
-                        ex = __ldg(rw + p.S_pad + (lane & 15));
+                        ex = __ldg(rw + (lane & 15));
                     }
                     if (is_front) { cgj = gj + 1 + adv; cw[1] = m; }
                 }
@@ -598,7 +579,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                         }
                     } else {
                         int plen;
-                        const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen);
+                        const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, p.cas_first != 0);
                         my_probes++;
                         my_max_probe = max(my_max_probe, plen);
                         if (res < 0) {
@@ -643,7 +624,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 int32_t cbal[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                const bool ok = cand && model_step<MODEL>(cop, creg, cbal, p.read_bal, neg_ok != 0, gj, w[1], p.set_need);
+                const bool ok = cand && model_step<MODEL>(cop, creg, cbal, nullptr, neg_ok != 0, w[1]);
 #pragma unroll
                 for (int i = 1; i < KW; ++i) if (i == cr.word) cw[i] += 1ull << shift;
                 cw[0] = KEY_VALID | ((uint64_t)(uint32_t)gj << 32) |
@@ -651,7 +632,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 int is_new = 0;
                 if (ok) {
                     int plen;
-                    const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen);
+                    const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, p.cas_first != 0);
                     my_probes++;
                     my_max_probe = max(my_max_probe, plen);
                     if (res < 0) {
@@ -678,6 +659,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 }
             }
         }
+        if (lane == 0 && n_done) atomicAdd(&sh.n_exp, n_done);
     }
     // ---- flush statistics -------------------------------------------------------------------------
     for (int o = 16; o > 0; o >>= 1) {
