@@ -101,10 +101,16 @@ typedef struct jtb_model {
     int32_t negative_balances_ok;         /* bank: (:negative-balances? test), core.clj:217-219     */
 } jtb_model;
 
+/* By default the search linearizes a consistent candidate READ immediately and exclusively ("eager
+ * reads": a read never changes the model state, so verdict and witness are unchanged while the number
+ * of configurations drops by an order of magnitude).  Knossos does not do this; set this flag to visit
+ * exactly the configurations Knossos' WGL would. */
+#define JTB_OPT_NO_EAGER_READS 1
+
 /* Options for a context.  Zero-initialise, then set what you need. */
 typedef struct jtb_opts {
     int32_t  device;            /* CUDA device ordinal for this context                              */
-    int32_t  reserved0;
+    int32_t  flags;             /* JTB_OPT_* bits                                                     */
     uint64_t table_bytes;       /* visited-config table size in HBM (0 = default 4 GiB)              */
     uint64_t max_configs;       /* search budget: stop with JTB_UNKNOWN after this many (0 = table)   */
     uint32_t time_budget_ms;    /* 0 = unlimited                                                      */

@@ -6,6 +6,7 @@ import ctypes as C
 from .history import MAX_ACCOUNTS  # noqa: F401  (re-exported for convenience)
 
 ABI_VERSION = 1
+OPT_NO_EAGER_READS = 1
 
 CAUSE_NONE, CAUSE_TABLE_FULL, CAUSE_BUDGET, CAUSE_TOO_WIDE = 0, 1, 2, 3
 CAUSE_NAME = {0: None, 1: "table-full", 2: "budget", 3: "too-wide"}
@@ -15,7 +16,7 @@ BANK_ERR_NAME = {1: "unexpected-key", 2: "nil-balance", 3: "wrong-total", 4: "ne
 
 
 class COpts(C.Structure):
-    _fields_ = [("device", C.c_int32), ("reserved0", C.c_int32), ("table_bytes", C.c_uint64),
+    _fields_ = [("device", C.c_int32), ("flags", C.c_int32), ("table_bytes", C.c_uint64),
                 ("max_configs", C.c_uint64), ("time_budget_ms", C.c_uint32),
                 ("search_ctas", C.c_uint32)]
 

@@ -284,6 +284,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.time_budget_ns = (unsigned long long)ctx->opts.time_budget_ms * 1000000ull;
             p.deque_cap = deque_cap;
             p.cas_first = getenv("JTB_CAS_FIRST") ? atoi(getenv("JTB_CAS_FIRST")) : 0;
+            p.eager_reads = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? 0 : 1;
             int rc;
             if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem);
             else if (m->kind == JTB_MODEL_SET) rc = launch_wgl<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem);

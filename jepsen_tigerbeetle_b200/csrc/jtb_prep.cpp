@@ -388,6 +388,9 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
             if (t.ops[i].crashed) continue;
             gid[i] = (int32_t)out.ops.size();
             out.ops.push_back(resolve(h, m, t.ops[i].ret_ev, out));
+            // reads carry their invocation position: the eager-read rule picks the EARLIEST-invoked
+            // consistent read, a choice that does not depend on slot numbering (oracle: first in list order)
+            if ((out.ops.back().x & 0xff) == JTB_F_READ) out.ops.back().w = t.ops[i].inv_pos;
         }
         (void)op_base;
         // class records

@@ -76,6 +76,7 @@ struct WglParams {
     unsigned long long time_budget_ns;
     uint32_t deque_cap;     // entries in the CTA's shared-memory deque (power of two)
     int cas_first;          // probe with atom.cas first (experiment switch, env JTB_CAS_FIRST)
+    int eager_reads;        // linearize a consistent candidate read immediately and exclusively
 };
 
 constexpr uint64_t KEY_VALID = 1ull << 63;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             const unsigned size = sh.top - sh.bot;
             // Invariant: an entry is counted in `created` before any other CTA can see it, and `created`
             // is always advanced before `expanded`.  So flush before donating, when idle, and periodically.
-            const bool may_donate = stop == 2 || size > high || (h > t && size > 1);
+            const bool may_donate = stop == 2 || size > high || (h > t && size > WGL_WARPS);
             if ((acc_new | acc_exp) && (may_donate || (was_idle && size == 0) || ++acc_age >= 16)) {
                 if (acc_new) { atomicAdd(&ctrl->created, (unsigned long long)acc_new); __threadfence(); }
                 if (acc_exp) atomicAdd(&ctrl->expanded, (unsigned long long)acc_exp);
@@ -404,6 +405,8 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             pre_tail = ld_volatile(&ctrl->tail);
         }
 
+        // narrow phase (few entries): the step is on the search's critical path -> one round trip per insert
+        const bool cas_first = p.cas_first != 0 || n_batch <= 4;
         // ---- self-scheduled expansion: next staged entry, else one poll of my ring ticket ---------------
         bool polled = false;
         unsigned n_done = 0;
@@ -525,12 +528,39 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 n_new_total += n;
             };
 
+            // -- eager reads: a consistent read never changes the state, so if any candidate read is consistent
+            //    it is linearized immediately and exclusively (verdict- and witness-preserving: any path from
+            //    this config can be re-ordered to start with that read).  Not in Knossos; see DESIGN.md.
+            int eager_t = -1;
+            if (p.eager_reads && shard_alive) {
+                unsigned best_inv = 0xffffffffu;  // earliest-invoked consistent read seen by this lane
+                int best_t = -1;
+                for (int r = 0; r < cand_rounds; ++r) {
+                    const int t = r * 32 + lane;
+                    const int32_t* cell = row + ROW_EXTRA + t * SW;
+                    const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
+                    bool rd = op.x >= 0 && (op.x & 0xff) == JTB_F_READ && !((w[1] >> t) & 1ull);
+                    if (rd) {
+                        int32_t creg = preg;
+                        int32_t cbal[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+                        rd = model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
+                    }
+                    if (rd && (unsigned)op.w < best_inv) { best_inv = (unsigned)op.w; best_t = t; }
+                }
+                const unsigned mn = __reduce_min_sync(0xffffffffu, best_inv);
+                if (mn != 0xffffffffu) {
+                    const unsigned who = __ballot_sync(0xffffffffu, best_inv == mn);
+                    eager_t = __shfl_sync(0xffffffffu, best_t, __ffs(who) - 1);
+                }
+            }
             // -- candidates: ops in the open slots
             for (int r = 0; r < cand_rounds && shard_alive; ++r) {
                 const int t = r * 32 + lane;
                 const int32_t* cell = row + ROW_EXTRA + t * SW;
                 const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
-                const bool cand = op.x >= 0 && !((w[1] >> t) & 1ull);
+                const bool cand = op.x >= 0 && !((w[1] >> t) & 1ull) && (eager_t < 0 || eager_t == t);
                 int32_t creg = preg;
                 int32_t cbal[8];
 #pragma unroll
@@ -579,7 +609,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                         }
                     } else {
                         int plen;
-                        const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, p.cas_first != 0);
+                        const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
                         my_probes++;
                         my_max_probe = max(my_max_probe, plen);
                         if (res < 0) {
@@ -601,7 +631,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 push_children(is_new != 0, cw, cbal);
             }
             // -- candidates: next member of each crashed-op class
-            for (int r = 0; r < cls_rounds && shard_alive; ++r) {
+            for (int r = 0; r < cls_rounds && shard_alive && eager_t < 0; ++r) {
                 const int c = r * 32 + lane;
                 bool cand = c < ncls;
                 struct { int first, n, word, shift_width; } cr = {0, 0, 1, 0};
@@ -632,7 +662,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 int is_new = 0;
                 if (ok) {
                     int plen;
-                    const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, p.cas_first != 0);
+                    const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
                     my_probes++;
                     my_max_probe = max(my_max_probe, plen);
                     if (res < 0) {

@@ -80,9 +80,10 @@ class Context:
     """One checker context = one CUDA device + stream + cached device buffers (`jtb_ctx`)."""
 
     def __init__(self, device: int = 0, table_bytes: int = 0, max_configs: int = 0,
-                 time_budget_ms: int = 0, search_ctas: int = 0) -> None:
+                 time_budget_ms: int = 0, search_ctas: int = 0, eager_reads: bool = True) -> None:
         L = lib()
-        opts = abi.COpts(device, 0, table_bytes, max_configs, time_budget_ms, search_ctas)
+        flags = 0 if eager_reads else abi.OPT_NO_EAGER_READS
+        opts = abi.COpts(device, flags, table_bytes, max_configs, time_budget_ms, search_ctas)
         self._h = L.jtb_create(C.byref(opts))
         if not self._h:
             raise NativeError("jtb_create failed: no CUDA device available (no CPU fallback)")

@@ -36,12 +36,13 @@ def lib() -> C.CDLL:
 
 
 def check_linearizable(h: FlatHistory, model: CModel, algo: int = ALGO_WGL_COMPACT,
-                       max_configs: int = 0, canon_info: bool = True, n_threads: int = 1) -> dict:
+                       max_configs: int = 0, canon_info: bool = True, n_threads: int = 1,
+                       eager_reads: bool = False) -> dict:
     ch = as_c_history(h)
     shards = (abi.CLinShard * h.n_shards)()
     res = abi.CLinResult()
     rc = lib().jtbo_check_linearizable(C.byref(ch), C.byref(model), algo, C.c_uint64(max_configs),
-                                       int(canon_info), n_threads, shards, C.byref(res))
+                                       int(bool(canon_info)) | (2 if eager_reads else 0), n_threads, shards, C.byref(res))
     if rc != 0:
         raise RuntimeError(lib().jtbo_last_error().decode())
     return {

@@ -264,10 +264,15 @@ struct Linear {
 // ALGO_WGL / ALGO_WGL_COMPACT  (knossos.wgl)
 struct WGL {
     const Shard& sh;
-    bool compact, canon;
+    bool compact, canon, eager;
     uint64_t max_configs;
-    WGL(const Shard& s, bool compact_, bool canon_, uint64_t mc)
-        : sh(s), compact(compact_), canon(canon_), max_configs(mc) {}
+    // eager: "eager reads" reduction (NOT in Knossos; mirrors the device search so that exhaustive config
+    // counts can be compared): a consistent read never changes the state, so when some candidate read is
+    // consistent with the current config it is linearized immediately and EXCLUSIVELY (no sibling is
+    // explored).  Sound for verdict and witness: any path from the config can be re-ordered to start with
+    // that read (it stays enabled, states are unchanged, the frontier can only move forward).
+    WGL(const Shard& s, bool compact_, bool canon_, uint64_t mc, bool eager_ = false)
+        : sh(s), compact(compact_), canon(canon_), eager(eager_), max_configs(mc) {}
 
     Verdict run() {
         Verdict v;
@@ -314,7 +319,7 @@ struct WGL {
         std::vector<int> ret_rank(n, -1);
         for (int j = 0; j < n_ret; ++j) ret_rank[sh.rets[j]] = j;
 
-        struct Frame { int op; State st; int rj; uint64_t mask; };
+        struct Frame { int op; State st; int rj; uint64_t mask; bool exclusive; };
         std::vector<Frame> stack;
         State st = sh.init;
         SetState ss;
@@ -339,9 +344,23 @@ struct WGL {
         };
 
         int entry = nxt[HEAD];
+        bool fresh = true;        // just arrived at a config (eager-read scan pending)
+        int only = -1;            // eager: the single call entry this config may linearize
+        bool force_back = false;  // eager: the exclusive child is exhausted -> backtrack
         while (true) {
             if (n_lin_completed == n_ret) break;  // every :ok op linearized -> valid
-            if (entry >= 0 && !(entry & 1)) {
+            if (eager && fresh) {
+                fresh = false;
+                only = -1;
+                for (int e = nxt[HEAD]; e >= 0 && !(e & 1); e = nxt[e]) {
+                    const Op& o = sh.ops[e >> 1];
+                    if (o.f != JTB_F_READ || o.crashed) continue;
+                    State tmp = st;
+                    if (step(sh, o, tmp, &ss)) { only = e; break; }
+                }
+                if (only >= 0) entry = only;
+            }
+            if (!force_back && entry >= 0 && !(entry & 1)) {
                 // ---- call entry: try to linearize it
                 const int i = entry >> 1;
                 const Op& o = sh.ops[i];
@@ -366,7 +385,8 @@ struct WGL {
                     v.probes++;
                     if (cache.insert(key.data())) {
                         v.configs++;
-                        stack.push_back(Frame{i, st, rj, mask});
+                        stack.push_back(Frame{i, st, rj, mask, only >= 0});
+                        fresh = true;
                         st = st2; rj = rj2; mask = mask2;
                         if (rj > max_rj) max_rj = rj;
                         if (!o.crashed) { n_lin_completed++; unlink(2 * i + 1); }
@@ -382,10 +402,9 @@ struct WGL {
                     lin[i >> 6] &= ~(1ull << (i & 63));
                     if (o.crashed) crashbits[crash_no[i] >> 6] &= ~(1ull << (crash_no[i] & 63));
                     if (sh.model->kind == JTB_MODEL_SET) unstep_set(o, &ss);
-                } else if (eligible && sh.model->kind == JTB_MODEL_SET && o.f == JTB_F_ADD) {
-                    // step() never fails for adds; nothing to undo
                 }
-                entry = nxt[entry];
+                if (only >= 0) force_back = true;  // the exclusive child was already visited
+                else entry = nxt[entry];
             } else {
                 // ---- return entry (or end of list): an un-linearized op has returned -> backtrack
                 if (stack.empty()) {
@@ -409,6 +428,8 @@ struct WGL {
                 relink(2 * i);
                 if (!o.crashed) relink(2 * i + 1);
                 entry = nxt[2 * i];
+                only = -1;
+                force_back = fr.exclusive;  // an exclusive child has no siblings: keep backtracking
             }
         }
         return v;
@@ -437,7 +458,8 @@ extern "C" {
 const char* jtbo_last_error(void) { return g_err.c_str(); }
 
 // algo: 0 brute, 1 linear, 2 wgl (full-bitset cache), 3 wgl compact (timed baseline)
-// canon_info: linearize crashed ops of one class (same f/value) in invocation order only
+// canon_info: bit 0 = linearize crashed ops of one class (same f/value) in invocation order only;
+//             bit 1 = eager reads (see WGL::eager; not part of Knossos)
 // n_threads: shards are checked in parallel, one thread per shard at a time (independent/checker)
 int jtbo_check_linearizable(const jtb_history* h, const jtb_model* m, int algo, uint64_t max_configs,
                             int canon_info, int n_threads, jtb_lin_shard* shards, jtb_lin_result* out) {
@@ -456,8 +478,8 @@ int jtbo_check_linearizable(const jtb_history* h, const jtb_model* m, int algo, 
                     switch (algo) {
                     case ALGO_BRUTE: v = Brute(sh).run(); break;
                     case ALGO_LINEAR: v = Linear(sh, max_configs).run(); break;
-                    case ALGO_WGL: v = WGL(sh, false, canon_info != 0, max_configs).run(); break;
-                    case ALGO_WGL_COMPACT: v = WGL(sh, true, canon_info != 0, max_configs).run(); break;
+                    case ALGO_WGL: v = WGL(sh, false, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
+                    case ALGO_WGL_COMPACT: v = WGL(sh, true, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
                     default: throw std::runtime_error("unknown algo");
                     }
                     fill(sh, v, &shards[s]);

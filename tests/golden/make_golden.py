@@ -42,9 +42,13 @@ def main():
         r = oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT)
         r2 = oracle.check_linearizable(h, m, oracle.ALGO_WGL)
         assert [(s["valid"], s["witness_index"]) for s in r["shards"]] == [(s["valid"], s["witness_index"]) for s in r2["shards"]]
+        re_ = oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT, eager_reads=True)
+        assert [(s["valid"], s["witness_index"]) for s in r["shards"]] == [(s["valid"], s["witness_index"]) for s in re_["shards"]]
+        exhaustive = r["valid"] == H.INVALID and h.n_shards == 1
         lin.append({"spec": spec, "valid": r["valid"],
                     "shards": [{k: s[k] for k in ("valid", "witness_index", "previous_ok_index")} for s in r["shards"]],
-                    "configs_if_exhaustive": r["configs"] if r["valid"] == H.INVALID and h.n_shards == 1 else None})
+                    "configs_if_exhaustive": r["configs"] if exhaustive else None,          # knossos-exact space
+                    "configs_if_exhaustive_eager": re_["configs"] if exhaustive else None})  # with eager reads
     sf = []
     for spec in SF_SPECS:
         h = synth.generate(synth.SynthSpec(**spec))

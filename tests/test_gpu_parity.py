@@ -39,7 +39,7 @@ def test_kats(gpu_ctx, oracle_mod, name, model, text, expect, witness):
     assert g["valid"] == expect
     if expect == H.INVALID and witness is not None:
         assert g["shards"][0]["witness_index"] == witness
-    same_verdict(g, oracle_mod.check_linearizable(h, model_for(model), 3))
+    same_verdict(g, oracle_mod.check_linearizable(h, model_for(model), 3, eager_reads=True))
 
 
 def test_bank_negative_balances_forbidden(gpu_ctx):
@@ -56,7 +56,7 @@ def test_random_small(gpu_ctx, oracle_mod, model):
         h = synth.generate(spec)
         m = model_for(model)
         g = gpu_ctx.check_linearizable(h, m)
-        o = oracle_mod.check_linearizable(h, m, 3)
+        o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
         same_verdict(g, o)
         if o["valid"] == H.INVALID:
             assert g["configs"] == o["configs"], (model, seed)
@@ -70,7 +70,7 @@ def test_config_c2(gpu_ctx, oracle_mod, p_info, stale):
         h = synth.config_c2(seed=seed, p_info=p_info, stale_read=stale)
         m = model_for("cas-register")
         g = gpu_ctx.check_linearizable(h, m)
-        o = oracle_mod.check_linearizable(h, m, 3)
+        o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
         same_verdict(g, o)
         if o["valid"] == H.INVALID:
             assert g["configs"] == o["configs"]
@@ -82,7 +82,7 @@ def test_config_c3_lite(gpu_ctx, oracle_mod, stale):
     h = synth.generate(synth.SynthSpec("bank", 10000, 32, 1, tau_think_ns=20e6, stale_read=stale))
     m = model_for("bank")
     g = gpu_ctx.check_linearizable(h, m)
-    o = oracle_mod.check_linearizable(h, m, 3)
+    o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
     same_verdict(g, o)
     if stale:
         assert o["valid"] == H.INVALID and g["configs"] == o["configs"]
@@ -94,7 +94,7 @@ def test_bank_with_crashed_transfers(gpu_ctx, oracle_mod):
                                            stale_read=seed == 2))
         m = model_for("bank")
         g = gpu_ctx.check_linearizable(h, m)
-        o = oracle_mod.check_linearizable(h, m, 3)
+        o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
         same_verdict(g, o)
 
 
@@ -103,13 +103,13 @@ def test_multi_shard(gpu_ctx, oracle_mod):
     h = synth.generate(synth.SynthSpec("cas-register", 4000, 64, 5, p_info=0.1, n_keys=8, grouped_keys=True))
     m = model_for("cas-register")
     g = gpu_ctx.check_linearizable(h, m)
-    o = oracle_mod.check_linearizable(h, m, 3, n_threads=4)
+    o = oracle_mod.check_linearizable(h, m, 3, n_threads=4, eager_reads=True)
     same_verdict(g, o)
     assert g["valid"] == H.VALID
     h = synth.generate(synth.SynthSpec("cas-register", 4000, 64, 5, p_info=0.1, n_keys=8, grouped_keys=True,
                                        stale_read=True))
     g = gpu_ctx.check_linearizable(h, m)
-    o = oracle_mod.check_linearizable(h, m, 3, n_threads=4)
+    o = oracle_mod.check_linearizable(h, m, 3, n_threads=4, eager_reads=True)
     same_verdict(g, o)
     assert g["n_failures"] == o["n_failures"]
 
@@ -121,7 +121,7 @@ def test_set_model_keyed_c4_lite(gpu_ctx, oracle_mod):
                                            tau_think_ns=5e6))
         m = model_for("set")
         g = gpu_ctx.check_linearizable(h, m)
-        o = oracle_mod.check_linearizable(h, m, 3, n_threads=4)
+        o = oracle_mod.check_linearizable(h, m, 3, n_threads=4, eager_reads=True)
         same_verdict(g, o)
         if stale:
             assert o["valid"] == H.INVALID
@@ -211,3 +211,20 @@ def test_checker_protocol_end_to_end(gpu_ctx):
     assert rb["SI"]["valid?"] is True          # totals are preserved by a stale read ...
     assert rb["linear"]["valid?"] is False     # ... but the history is not linearizable
     assert rb["valid?"] is False and rb["linear"]["op"]["index"] >= 0
+
+
+def test_knossos_exact_mode_without_eager_reads(oracle_mod):
+    """JTB_OPT_NO_EAGER_READS: the device visits exactly the configurations knossos.wgl's search space holds."""
+    from jepsen_tigerbeetle_b200 import native
+    with native.Context(eager_reads=False) as ctx:
+        for model, spec in (("bank", synth.SynthSpec("bank", 3000, 16, 3, tau_think_ns=10e6, stale_read=True)),
+                            ("cas-register", synth.SynthSpec("cas-register", 1000, 16, 1, n_values=30, stale_read=True)),
+                            ("set", synth.SynthSpec("set", 800, 8, 2, stale_read=True, tau_think_ns=5e6))):
+            h = synth.generate(spec)
+            m = model_for(model)
+            g = ctx.check_linearizable(h, m)
+            o = oracle_mod.check_linearizable(h, m, 3)          # plain WGL, no reduction
+            same_verdict(g, o)
+            assert o["valid"] == H.INVALID and g["configs"] == o["configs"], model
+            e = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
+            assert e["configs"] <= o["configs"]

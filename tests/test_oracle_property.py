@@ -92,3 +92,21 @@ def test_prefix_closure(oracle_mod):
                             hp.c[sl].copy(), hp.payload_off[sl].copy(), hp.payload_len[sl].copy(), hp.payload,
                             np.array([0, cut], np.int64), hp.key_ids)
         assert oracle_mod.check_linearizable(hp2, m, 3)["valid"] == H.VALID
+
+
+@pytest.mark.parametrize("model", list(MODELS))
+def test_eager_reads_preserve_verdict_and_witness(oracle_mod, model):
+    """The device's "eager reads" reduction (restated in the oracle as an option) never changes the answer."""
+    for seed in range(40):
+        spec = synth.SynthSpec(model, n_ops=9 if seed < 20 else 200, n_clients=3 if seed < 20 else 5, seed=seed,
+                               p_info=0.15 if seed % 2 else 0.0, stale_read=seed % 3 != 0, stale_by=2 + seed % 3,
+                               n_values=3, n_accounts=3 if seed < 20 else 8, tau_think_ns=0 if seed < 20 else 4e6)
+        h = synth.generate(spec)
+        m = MODELS[model]() if not (model == "bank" and seed < 20) else H.make_model(H.MODEL_BANK, accounts=range(1, 4))
+        plain = oracle_mod.check_linearizable(h, m, 3)
+        eager_c = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
+        eager_f = oracle_mod.check_linearizable(h, m, 2, eager_reads=True)
+        assert verdict(plain) == verdict(eager_c) == verdict(eager_f), (model, seed)
+        assert eager_c["configs"] <= plain["configs"] or plain["valid"] != H.INVALID
+        if seed < 20:
+            assert verdict(oracle_mod.check_linearizable(h, m, 0)) == verdict(eager_c)  # vs brute force
