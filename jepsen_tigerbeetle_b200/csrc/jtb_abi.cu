@@ -71,21 +71,27 @@ int upload(jtb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
     return 0;
 }
 
-template <int MODEL, int KW>
-int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem) {
-    auto k = wgl_search_kernel<MODEL, KW>;
+template <int MODEL, int KW, int MINB>
+int launch_wgl_b(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem) {
+    auto k = wgl_search_kernel<MODEL, KW, MINB>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, WGL_THREADS, smem, ctx->stream>>>(p, neg_ok);
     CK(cudaGetLastError());
     return 0;
 }
 
+template <int MODEL, int KW>
+int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem, int ctas_per_sm) {
+    return ctas_per_sm >= 4 ? launch_wgl_b<MODEL, KW, 4>(ctx, p, neg_ok, grid, smem)
+                            : launch_wgl_b<MODEL, KW, 3>(ctx, p, neg_ok, grid, smem);
+}
+
 template <int MODEL>
-int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid, size_t smem) {
+int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid, size_t smem, int ctas_per_sm) {
     switch (kw) {
-    case 2: return launch_wgl<MODEL, 2>(ctx, p, neg_ok, grid, smem);
-    case 4: return launch_wgl<MODEL, 4>(ctx, p, neg_ok, grid, smem);
-    case 8: return launch_wgl<MODEL, 8>(ctx, p, neg_ok, grid, smem);
+    case 2: return launch_wgl<MODEL, 2>(ctx, p, neg_ok, grid, smem, ctas_per_sm);
+    case 4: return launch_wgl<MODEL, 4>(ctx, p, neg_ok, grid, smem, ctas_per_sm);
+    case 8: return launch_wgl<MODEL, 8>(ctx, p, neg_ok, grid, smem, ctas_per_sm);
     }
     ctx->err = "unsupported key width";
     return -1;
@@ -222,7 +228,10 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         while ((size_t)deque_cap * EW * 8 > 48 * 1024) deque_cap >>= 1;
         const uint32_t stage_cap = std::max(deque_cap, worst_push);
         const size_t smem = (size_t)(deque_cap + WGL_BATCH) * EW * 8;   // deque + staged batch
-        int ctas_per_sm = (int)std::min<size_t>(4, (220 * 1024) / (smem + 1024));
+        // eager-read searches are small and latency-bound: 3 CTAs/SM (no register spills) wins; the
+        // Knossos-exact space is throughput-bound: 4 CTAs/SM (measured A/B)
+        const int want_ctas = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? 4 : 3;
+        int ctas_per_sm = (int)std::min<size_t>(want_ctas, (220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, ctas_per_sm);
         const int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;
         const uint64_t per_step_push = (uint64_t)grid * stage_cap;  // worst case children of one step of every CTA
@@ -285,10 +294,12 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.deque_cap = deque_cap;
             p.cas_first = getenv("JTB_CAS_FIRST") ? atoi(getenv("JTB_CAS_FIRST")) : 0;
             p.eager_reads = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? 0 : 1;
+            p.max_chain = getenv("JTB_CHAIN") ? atoi(getenv("JTB_CHAIN")) : 0;
+            p.narrow_cas = getenv("JTB_NARROW_CAS") ? atoi(getenv("JTB_NARROW_CAS")) : 0;
             int rc;
-            if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem);
-            else if (m->kind == JTB_MODEL_SET) rc = launch_wgl<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem);
-            else rc = launch_wgl_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, grid, smem);
+            if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem, ctas_per_sm);
+            else if (m->kind == JTB_MODEL_SET) rc = launch_wgl<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem, ctas_per_sm);
+            else rc = launch_wgl_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, grid, smem, ctas_per_sm);
             if (rc) { free_tmp(); return rc; }
             CK(cudaMemcpyAsync(&hc, ctx->ctrl.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));

@@ -77,6 +77,8 @@ struct WglParams {
     uint32_t deque_cap;     // entries in the CTA's shared-memory deque (power of two)
     int cas_first;          // probe with atom.cas first (experiment switch, env JTB_CAS_FIRST)
     int eager_reads;        // linearize a consistent candidate read immediately and exclusively
+    int max_chain;          // depth-first continuations a warp may take per step (experiment switch JTB_CHAIN)
+    int narrow_cas;         // CAS-first when the CTA's batch is narrow (experiment switch JTB_NARROW_CAS)
 };
 
 constexpr uint64_t KEY_VALID = 1ull << 63;
@@ -240,7 +242,10 @@ struct EntryLayout {
 constexpr int WGL_WARPS = 8;
 constexpr int WGL_THREADS = WGL_WARPS * 32;
 constexpr unsigned WGL_MAX_DONATE = 64;       // per step, when donating to hungry warps
-constexpr unsigned WGL_BATCH = 32;            // deque entries popped per CTA step; warps self-schedule over them
+#ifndef JTB_BATCH
+#define JTB_BATCH 32
+#endif
+constexpr unsigned WGL_BATCH = JTB_BATCH;     // deque entries popped per CTA step; warps self-schedule over them
 
 struct CtaShared {
     int stop;
@@ -260,8 +265,10 @@ struct CtaShared {
 
 __device__ __forceinline__ uint64_t ld_volatile64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 
-template <int MODEL, int KW>
-__global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglParams p, const int neg_ok) {
+// MINB = resident CTAs per SM the register budget is cut for: 4 (64 regs, 32 warps/SM) is best for large,
+// throughput-bound searches; 3 (78 regs, no spills) is 11-17 % faster on small latency-bound ones (measured A/B).
+template <int MODEL, int KW, int MINB>
+__global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const WglParams p, const int neg_ok) {
     using L = EntryLayout<MODEL, KW>;
     constexpr int EW = L::EW;
     extern __shared__ __align__(16) uint64_t s_deque[];  // deque_cap * EW words, then WGL_BATCH * EW staging
@@ -406,18 +413,26 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
         }
 
         // narrow phase (few entries): the step is on the search's critical path -> one round trip per insert
-        const bool cas_first = p.cas_first != 0 || n_batch <= 4;
+        const bool cas_first = p.cas_first != 0 || (p.narrow_cas && n_batch <= 4);
         // ---- self-scheduled expansion: next staged entry, else one poll of my ring ticket ---------------
         bool polled = false;
         unsigned n_done = 0;
+        [[maybe_unused]] int chain = 0;  // consecutive single-child continuations taken without a barrier
+        bool have_chain = false;
+        uint64_t w[KW];
+        int32_t pbal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (;;) {
-            uint64_t w[KW];
-            int32_t pbal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             bool have = false;
-            unsigned idx = 0;
-            if (lane == 0) idx = atomicAdd(&sh.batch_next, 1u);
-            idx = __shfl_sync(0xffffffffu, idx, 0);
-            if (idx < n_batch) {
+            unsigned idx = 0xffffffffu;
+            if (have_chain) {
+                have = true;        // w / pbal already hold my own single child (depth-first continuation)
+                have_chain = false;
+            } else {
+                if (lane == 0) idx = atomicAdd(&sh.batch_next, 1u);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+            }
+            if (have) {
+            } else if (idx < n_batch) {
                 const uint64_t* e = &s_batch[(size_t)idx * EW];
 #pragma unroll
                 for (int i = 0; i < KW; ++i) w[i] = e[i];
@@ -472,6 +487,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
             const int rslot = __shfl_sync(0xffffffffu, extra, 13);
             const bool shard_alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
             int n_new_total = 0, n_new_local = 0;
+            unsigned last_base = 0xffffffffu;   // deque index of the most recent local push
 
             auto push_children = [&](bool is_new, const uint64_t (&cw)[KW], const int32_t (&cbal)[8]) {
                 const unsigned newm = __ballot_sync(0xffffffffu, is_new);
@@ -492,6 +508,7 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                 base = __shfl_sync(0xffffffffu, base, 0);
                 to_ring = __shfl_sync(0xffffffffu, to_ring, 0);
                 const unsigned my = __popc(newm & ((1u << lane) - 1));
+                last_base = to_ring ? 0xffffffffu : base;
                 if (!to_ring) {
                     if (is_new) {
                         uint64_t* e = &s_deque[(size_t)((base + my) & cap_mask) * EW];
@@ -688,6 +705,36 @@ __global__ void __launch_bounds__(WGL_THREADS, 4) wgl_search_kernel(const WglPar
                     }
                 }
             }
+#ifdef JTB_ENABLE_CHAIN
+            // ---- depth-first continuation: exactly one new child, pushed locally and still on top of the
+            //      deque -> take it back (speculative read, then CAS on top) and expand it right away.
+            if (n_new_total == 1 && last_base != 0xffffffffu && chain < p.max_chain) {
+                const uint64_t* e = &s_deque[(size_t)(last_base & cap_mask) * EW];
+                uint64_t cw2[KW];
+                int32_t cb2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int i = 0; i < KW; ++i) cw2[i] = e[i];
+                if constexpr (L::HAS_BAL) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint64_t v = e[KW + i];
+                        cb2[2 * i] = (int32_t)(uint32_t)v;
+                        cb2[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+                    }
+                }
+                int got = 0;
+                if (lane == 0) got = atomicCAS(&sh.top, last_base + 1, last_base) == last_base + 1;
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (got) {
+#pragma unroll
+                    for (int i = 0; i < KW; ++i) w[i] = cw2[i];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pbal[i] = cb2[i];
+                    have_chain = true;
+                    ++chain;
+                }
+            }
+        #endif
         }
         if (lane == 0 && n_done) atomicAdd(&sh.n_exp, n_done);
     }

@@ -16,7 +16,7 @@ from . import abi
 from .history import CHistory, CModel, FlatHistory, as_c_history
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjtb_check.so")
+LIB_PATH = os.environ.get("JTB_LIB_PATH") or os.path.join(_HERE, "libjtb_check.so")  # env: A/B experiments only
 CSRC = os.path.join(_HERE, "csrc")
 _SOURCES = ["jtb_abi.cu", "jtb_prep.cpp"]
 _DEPS = _SOURCES + ["jtb_prep.h", "jtb_wgl.cuh", "jtb_scans.cuh", "jtb_table_bench.cuh"]
