@@ -247,6 +247,9 @@ int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n);
 /* ---- diagnostics: host preparation only (pairing, slots, tables) — no device work; returns seconds
  * or a negative value on malformed input.  Lets callers see the host share of time-to-verdict. */
 double jtb_prepare_seconds(const jtb_history* h, const jtb_model* m);
+/* same, also reporting the layout chosen: info[0..3] = key bytes, slot lanes (32|64), max crashed-op classes per
+ * shard, total completed ops (ranks) */
+double jtb_prepare_info(const jtb_history* h, const jtb_model* m, long long info[4]);
 
 /* ---- K2 in isolation: visited-table probe/insert microbenchmark (roofline evidence) ----------- *
  * Inserts n_keys pseudo-random 128-bit keys then probes them `rounds` times; returns device

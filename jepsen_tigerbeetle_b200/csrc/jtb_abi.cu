@@ -412,6 +412,14 @@ double jtb_prepare_seconds(const jtb_history* h, const jtb_model* m) {
     return now_s() - t0;
 }
 
+double jtb_prepare_info(const jtb_history* h, const jtb_model* m, long long info[4]) {
+    const double t0 = now_s();
+    Prepared P;
+    if (!prepare(h, m, P)) return -1.0;
+    info[0] = P.key_words * 8; info[1] = P.S_pad; info[2] = P.max_nc; info[3] = P.n_ranks;
+    return now_s() - t0;
+}
+
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n) {
     if (!ctx) return -1;
     for (int i = 0; i < n && i < 16; ++i) out[i] = ctx->stats[i];

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
-           "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds"]
+           "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds", "jtb_prepare_info"]
 
 _lib = None
 _lock = threading.Lock()
@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
             L.jtb_struct_size.restype = C.c_long
             L.jtb_prepare_seconds.restype = C.c_double
             L.jtb_prepare_seconds.argtypes = [C.c_void_p, C.c_void_p]
+            L.jtb_prepare_info.restype = C.c_double
+            L.jtb_prepare_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             L.jtb_device_count.restype = C.c_int
             L.jtb_create.restype = C.c_void_p
             L.jtb_create.argtypes = [C.c_void_p]
@@ -176,6 +178,14 @@ def prepare_seconds(h: FlatHistory, model: CModel) -> float:
     """Host preparation time only (no GPU needed)."""
     ch = as_c_history(h)
     return lib().jtb_prepare_seconds(C.addressof(ch), C.addressof(model))
+
+
+def prepare_info(h: FlatHistory, model: CModel) -> dict:
+    """Host preparation only (no GPU needed): the layout the device search would use."""
+    ch = as_c_history(h)
+    info = (C.c_longlong * 4)()
+    sec = lib().jtb_prepare_info(C.addressof(ch), C.addressof(model), C.addressof(info))
+    return {"seconds": sec, "key_bytes": info[0], "slot_lanes": info[1], "max_classes": info[2], "ranks": info[3]}
 
 
 def device_count() -> int:

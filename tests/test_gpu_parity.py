@@ -228,3 +228,42 @@ def test_knossos_exact_mode_without_eager_reads(oracle_mod):
             assert o["valid"] == H.INVALID and g["configs"] == o["configs"], model
             e = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
             assert e["configs"] <= o["configs"]
+
+
+@pytest.mark.parametrize("model,n_clients,n_ops,think", [("cas-register", 48, 600, 4e6), ("bank", 40, 500, 6e6),
+                                                         ("set", 44, 500, 5e6)])
+def test_more_than_32_open_ops(gpu_ctx, oracle_mod, model, n_clients, n_ops, think):
+    """> 32 concurrently open ops: 64 slot lanes, two candidate rounds per expansion."""
+    from jepsen_tigerbeetle_b200 import native
+    for stale in (False, True):
+        h = synth.generate(synth.SynthSpec(model, n_ops, n_clients, 1 + stale, tau_think_ns=think, stale_read=stale,
+                                           n_values=6))
+        m = model_for(model)
+        assert native.prepare_info(h, m)["slot_lanes"] == 64
+        g = gpu_ctx.check_linearizable(h, m)
+        o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
+        same_verdict(g, o)
+        if o["valid"] == H.INVALID:
+            assert g["configs"] == o["configs"]
+
+
+@pytest.mark.parametrize("n_clients,n_ops,p_info,n_values,key_bytes", [(12, 900, 0.4, 14, 32), (8, 1500, 0.4, 24, 64)])
+def test_wide_keys_many_crashed_op_classes(gpu_ctx, oracle_mod, n_clients, n_ops, p_info, n_values, key_bytes):
+    """Hundreds of crashed-op classes: 32 B / 64 B keys (lock-bit slots), several class rounds per expansion."""
+    from jepsen_tigerbeetle_b200 import native
+    m = model_for("cas-register")
+    h = synth.generate(synth.SynthSpec("cas-register", n_ops, n_clients, 3, tau_think_ns=2e6, p_info=p_info,
+                                       n_values=n_values))
+    assert native.prepare_info(h, m)["key_bytes"] == key_bytes
+    g = gpu_ctx.check_linearizable(h, m)
+    assert g["key_bytes"] == key_bytes
+    same_verdict(g, oracle_mod.check_linearizable(h, m, 3, eager_reads=True))
+    assert g["valid"] == H.VALID
+    # an :ok read of a value nobody ever wrote, early in the history: invalid, exhaustive up to that read
+    reads = np.flatnonzero((h.type == 1) & (h.f == 0) & (h.a != H.NIL))
+    h.a[reads[3]] = 999
+    g = gpu_ctx.check_linearizable(h, m)
+    o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
+    same_verdict(g, o)
+    assert g["valid"] == H.INVALID and g["shards"][0]["witness_index"] == int(h.index[reads[3]])
+    assert g["configs"] == o["configs"]
