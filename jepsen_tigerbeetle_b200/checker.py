@@ -324,3 +324,135 @@ def compose(checkers: Mapping[str, Checker]) -> Compose:
 
 def independent_checker(inner: Checker, model: str | None = None) -> Independent:
     return Independent(inner, model)
+
+
+# =====================================================================================================
+# The ledger test's remaining (host-side, O(events)) checkers — SURVEY §8(f) N3.  In the reference these
+# are plain Clojure seq operations over the op maps with no arithmetic worth a kernel; they are restated
+# here on the host so that the whole `compose` map of tests/ledger.clj:363-367 can be served by this
+# package.  They consume op maps (not the flattened arrays: they need the :l-t ops and :final? flags).
+# =====================================================================================================
+def _is_client(op) -> bool:
+    p = op.get("process", op.get(":process"))
+    return isinstance(p, (int, np.integer)) and not isinstance(p, bool)
+
+
+def _g(op, name, default=None):
+    return op.get(name, op.get(":" + name, default))
+
+
+def _kw(x):
+    return x[1:] if isinstance(x, str) and x.startswith(":") else x
+
+
+def _txn_f(op):
+    """tests/ledger.clj:17-21 op->txn-f: the first micro-op's tag."""
+    v = _g(op, "value")
+    if not v:
+        return None
+    first = v[0] if isinstance(v, (list, tuple)) else None
+    return _kw(first[0]) if first else None
+
+
+def _freeze(x):
+    if isinstance(x, dict):
+        return tuple(sorted((k, _freeze(v)) for k, v in x.items()))
+    if isinstance(x, (list, tuple)):
+        return tuple(_freeze(v) for v in x)
+    if isinstance(x, (set, frozenset)):
+        return frozenset(_freeze(v) for v in x)
+    return x
+
+
+class UnexpectedOps(Checker):
+    """`(unexpected-ops)` — tests/ledger.clj:194-220: never-resolved invokes and :fail ops mark the
+    result :unknown ({:valid? :unknown :open-ops [...] :fail-ops [...]})."""
+
+    def check(self, test, history, opts=None) -> dict:
+        hist = [op for op in history if _is_client(op)]
+        end_time = _g(hist[-1], "time", 0) if hist else 0
+        open_by_process: dict = {}
+        for op in hist:  # knossos.history/unmatched-invokes
+            t = _kw(_g(op, "type"))
+            p = _g(op, "process")
+            if t == "invoke":
+                open_by_process[p] = op
+            else:
+                open_by_process.pop(p, None)
+        open_ops = sorted(open_by_process.values(), key=lambda o: _g(o, "index", 0))
+        opens = [[(end_time - _g(o, "time", 0)) / 1e6, o] for o in open_ops][::-1]  # util/nanos->ms, rseq
+        fails = [op for op in hist if _kw(_g(op, "type")) == "fail"]
+        out: dict = {"valid?": True}
+        if opens:
+            out.update({"valid?": "unknown", "open-ops": opens})
+        if fails:
+            out.update({"valid?": "unknown", "fail-ops": fails})
+        return out
+
+
+class LookupAllInvokedTransfers(Checker):
+    """`(lookup-all-invoked-transfers)` — tests/ledger.clj:222-252: every :final? :ok :l-t lookup must
+    contain the id of every invoked transfer."""
+
+    def check(self, test, history, opts=None) -> dict:
+        hist = [op for op in history if _is_client(op)]
+        invoked = set()
+        for op in hist:
+            if _txn_f(op) == "t" and _kw(_g(op, "type")) == "invoke":
+                for micro in _g(op, "value"):
+                    invoked.add(micro[1])
+        suspects = []
+        for op in hist:
+            if _txn_f(op) == "l-t" and _kw(_g(op, "type")) == "ok" and _g(op, "final?"):
+                ids = {micro[1] for micro in _g(op, "value")}
+                if invoked - ids:
+                    suspects.append(op)
+        out: dict = {"valid?": True}
+        if suspects:
+            out.update({"valid?": False, "suspect-final-lookups": suspects})
+        return out
+
+
+class FinalReads(Checker):
+    """`(final-reads)` — tests/ledger.clj:254-282: final reads (and final :l-t lookups) must exist and be
+    all equal: exactly one distinct :value among the :final? :ok :r ops, and among the :l-t ones."""
+
+    def check(self, test, history, opts=None) -> dict:
+        hist = [op for op in history if _is_client(op)]
+
+        def finals(tag):
+            return {_freeze(_g(op, "value")) for op in hist
+                    if _txn_f(op) == tag and _kw(_g(op, "type")) == "ok" and _g(op, "final?")}
+
+        reads, lookups = finals("r"), finals("l-t")
+        out: dict = {"valid?": True}
+        if len(reads) != 1:
+            out.update({"valid?": False, "unequal-final-reads": reads})
+        if len(lookups) != 1:
+            out.update({"valid?": False, "unequal-final-lookups": lookups})
+        return out
+
+
+def unexpected_ops() -> UnexpectedOps:
+    return UnexpectedOps()
+
+
+def lookup_all_invoked_transfers() -> LookupAllInvokedTransfers:
+    return LookupAllInvokedTransfers()
+
+
+def final_reads() -> FinalReads:
+    return FinalReads()
+
+
+def ledger_checker(checker_opts: Mapping[str, Any] | None = None, ctx: Context | None = None,
+                   linear: bool = True) -> Compose:
+    """The ledger test's checker (tests/ledger.clj:363-367) minus the gnuplot plotter, plus the
+    linearizability search the north-star adds:
+        {:SI (checker opts) :lookup-transfers ... :final-reads ... :unexpected-ops ... [:linear ...]}"""
+    cs: dict[str, Checker] = {"SI": bank_checker(checker_opts, ctx=ctx),
+                              "lookup-transfers": lookup_all_invoked_transfers(),
+                              "final-reads": final_reads(), "unexpected-ops": unexpected_ops()}
+    if linear:
+        cs["linear"] = linearizable({"model": "bank"}, ctx=ctx)
+    return compose(cs)

@@ -61,3 +61,42 @@ def test_flattener_accepts_both_bank_spellings():
     b = H.flatten_ops([{"type": "invoke", "f": "transfer", "process": 0,
                         "value": {"debit-acct": 1, "credit-acct": 2, "amount": 3}}], "bank")
     assert (a.a[0], a.b[0], a.c[0]) == (b.a[0], b.b[0], b.c[0]) == (3, 1, 2)
+
+
+# ---- the ledger test's host-side checkers (tests/ledger.clj:194-282) --------------------------------------
+def _t(i, p, typ, micro, final=False, t=None):
+    op = {"index": i, "process": p, "type": typ, "f": "txn", "value": micro, "time": t if t is not None else i * 1000}
+    if final:
+        op["final?"] = True
+    return op
+
+
+def test_unexpected_ops():
+    tr = [["t", 1, {"debit-acct": 1, "credit-acct": 2, "amount": 3}]]
+    h = [_t(0, 0, "invoke", tr), _t(1, 0, "ok", tr), {"index": 2, "process": "nemesis", "type": "info", "f": "kill", "value": None, "time": 2000}]
+    assert ck.unexpected_ops().check({}, h) == {"valid?": True}
+    h2 = h + [_t(3, 1, "invoke", tr, t=5_000_000), _t(4, 2, "invoke", tr, t=6_000_000), _t(5, 2, "fail", tr, t=9_000_000)]
+    r = ck.unexpected_ops().check({}, h2)
+    assert r["valid?"] == "unknown" and len(r["fail-ops"]) == 1
+    assert [o["index"] for _, o in r["open-ops"]] == [3] and r["open-ops"][0][0] == 4.0  # (9e6 - 5e6) ns -> ms
+
+
+def test_lookup_all_invoked_transfers_and_final_reads():
+    t1 = [["t", 1, {"debit-acct": 1, "credit-acct": 2, "amount": 3}]]
+    t2 = [["t", 2, {"debit-acct": 2, "credit-acct": 3, "amount": 1}]]
+    rd = [["r", a, {"credits-posted": 0, "debits-posted": 0}] for a in (1, 2)]
+    h = [_t(0, 0, "invoke", t1), _t(1, 0, "ok", t1), _t(2, 1, "invoke", t2), _t(3, 1, "info", t2),
+         _t(4, 0, "invoke", [["r", 1, None], ["r", 2, None]], final=True), _t(5, 0, "ok", rd, final=True),
+         _t(6, 1, "invoke", [["r", 1, None], ["r", 2, None]], final=True), _t(7, 1, "ok", rd, final=True),
+         _t(8, 0, "invoke", [["l-t", None, None]], final=True), _t(9, 0, "ok", [["l-t", 1, {}], ["l-t", 2, {}]], final=True)]
+    assert ck.lookup_all_invoked_transfers().check({}, h) == {"valid?": True}
+    assert ck.final_reads().check({}, h) == {"valid?": True}
+    h_bad = h[:-1] + [_t(9, 0, "ok", [["l-t", 1, {}]], final=True)]          # the crashed transfer 2 is missing
+    r = ck.lookup_all_invoked_transfers().check({}, h_bad)
+    assert r["valid?"] is False and [o["index"] for o in r["suspect-final-lookups"]] == [9]
+    rd2 = [["r", 1, {"credits-posted": 1, "debits-posted": 0}], ["r", 2, {"credits-posted": 0, "debits-posted": 0}]]
+    h_uneq = h[:7] + [_t(7, 1, "ok", rd2, final=True)] + h[8:]
+    r = ck.final_reads().check({}, h_uneq)
+    assert r["valid?"] is False and len(r["unequal-final-reads"]) == 2
+    r = ck.final_reads().check({}, h[:4])                                       # no final reads at all
+    assert r["valid?"] is False and r["unequal-final-reads"] == set() and r["unequal-final-lookups"] == set()
