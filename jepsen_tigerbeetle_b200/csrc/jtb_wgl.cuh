@@ -232,6 +232,175 @@ __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t 
     }
 }
 
+// One expansion, warp-synchronous: evaluates every candidate of the configuration (w, pbal), probes/inserts the
+// consistent children and hands the NEW ones to `push(is_new, key words, balances)` (called by all lanes, once per
+// candidate round).  Shared by the search kernels; `wit_cache` is a shared-memory filter for the witness atomicMax.
+template <int MODEL, int KW, typename Push>
+__device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, const int neg_ok, const uint64_t (&w)[KW],
+                                              const int32_t (&pbal)[8], const int lane, const bool cas_first,
+                                              unsigned long long* wit_cache, unsigned long long& my_probes,
+                                              int& my_max_probe, Push&& push) {
+    constexpr int SW = MODEL == JTB_MODEL_BANK ? 12 : MODEL == JTB_MODEL_SET ? 8 : 4;  // = slot_words(MODEL)
+    const int cand_rounds = p.S_pad / 32;
+    const int cls_rounds = (p.max_nc + 31) / 32;
+    const int gj = (int)((w[0] >> 32) & 0x3fffffffu);
+    const int32_t preg = (int32_t)(uint32_t)w[0];
+    const int32_t* row = p.rows + (size_t)gj * p.row_words;
+    const int32_t extra = __ldg(row + (lane & 15));
+    const int fr_pos = __shfl_sync(0xffffffffu, extra, 8);
+    const int shard = __shfl_sync(0xffffffffu, extra, 9);
+    const int gj_end = __shfl_sync(0xffffffffu, extra, 10);
+    const int cls_base = __shfl_sync(0xffffffffu, extra, 11);
+    const int ncls = __shfl_sync(0xffffffffu, extra, 12);
+    const int rslot = __shfl_sync(0xffffffffu, extra, 13);
+    const bool shard_alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
+    // -- eager reads: a consistent read never changes the state, so if any candidate read is consistent
+    //    it is linearized immediately and exclusively (verdict- and witness-preserving: any path from
+    //    this config can be re-ordered to start with that read).  Not in Knossos; see DESIGN.md.
+    int eager_t = -1;
+    if (p.eager_reads && shard_alive) {
+        unsigned best_inv = 0xffffffffu;  // earliest-invoked consistent read seen by this lane
+        int best_t = -1;
+        for (int r = 0; r < cand_rounds; ++r) {
+            const int t = r * 32 + lane;
+            const int32_t* cell = row + ROW_EXTRA + t * SW;
+            const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
+            bool rd = op.x >= 0 && (op.x & 0xff) == JTB_F_READ && !((w[1] >> t) & 1ull);
+            if (rd) {
+                int32_t creg = preg;
+                int32_t cbal[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+                rd = model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
+            }
+            if (rd && (unsigned)op.w < best_inv) { best_inv = (unsigned)op.w; best_t = t; }
+        }
+        const unsigned mn = __reduce_min_sync(0xffffffffu, best_inv);
+        if (mn != 0xffffffffu) {
+            const unsigned who = __ballot_sync(0xffffffffu, best_inv == mn);
+            eager_t = __shfl_sync(0xffffffffu, best_t, __ffs(who) - 1);
+        }
+    }
+    // -- candidates: ops in the open slots
+    for (int r = 0; r < cand_rounds && shard_alive; ++r) {
+        const int t = r * 32 + lane;
+        const int32_t* cell = row + ROW_EXTRA + t * SW;
+        const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
+        const bool cand = op.x >= 0 && !((w[1] >> t) & 1ull) && (eager_t < 0 || eager_t == t);
+        int32_t creg = preg;
+        int32_t cbal[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+        bool ok = cand && model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
+        const bool is_front = t == rslot;
+        uint64_t cw[KW];
+#pragma unroll
+        for (int i = 0; i < KW; ++i) cw[i] = w[i];
+        int cgj = gj;
+        // frontier advance, warp-cooperative, for the child that linearizes the frontier op
+        const unsigned front_ok = __ballot_sync(0xffffffffu, ok && is_front);
+        if (front_ok) {
+            uint64_t m = w[1];
+            int adv = 0;
+            const int32_t* rw = row;
+            int32_t ex = extra;
+            for (;;) {
+                const int32_t word = __shfl_sync(0xffffffffu, ex, lane >> 2);
+                const int sl = (word >> (8 * (lane & 3))) & 0xff;
+                const bool setb = sl != 0xff && ((m >> sl) & 1ull);
+                const unsigned peers = __match_any_sync(0xffffffffu, sl);
+                const bool pass = setb && (peers & ((1u << lane) - 1)) == 0;
+                const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                const int n = pm == 0xffffffffu ? 32 : __ffs(~pm) - 1;
+                const uint64_t clr = (lane < n) ? (1ull << sl) : 0ull;
+                const uint32_t clo = __reduce_or_sync(0xffffffffu, (uint32_t)clr);
+                const uint32_t chi = __reduce_or_sync(0xffffffffu, (uint32_t)(clr >> 32));
+                m &= ~((uint64_t)clo | ((uint64_t)chi << 32));
+                adv += n;
+                if (n < 32) break;
+                rw += (size_t)32 * p.row_words;
+                ex = __ldg(rw + (lane & 15));
+            }
+            if (is_front) { cgj = gj + 1 + adv; cw[1] = m; }
+        }
+        if (ok && !is_front) cw[1] |= 1ull << t;
+        cw[0] = KEY_VALID | ((uint64_t)(uint32_t)cgj << 32) |
+                ((MODEL == JTB_MODEL_BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
+        int is_new = 0;
+        if (ok) {
+            if (cgj >= gj_end) {
+                // every :ok op of the shard is linearized -> VALID
+                if (atomicExch(&p.shard_found[shard], 1) == 0) {
+                    if (atomicSub(&ctrl->n_undecided, 1) == 1) atomicCAS(&ctrl->stop, 0, 1);
+                }
+            } else {
+                int plen;
+                const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
+                my_probes++;
+                my_max_probe = max(my_max_probe, plen);
+                if (res < 0) {
+                    atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
+                    atomicCAS(&ctrl->stop, 0, 2);
+                }
+                is_new = res > 0;
+                if (is_new && cgj > gj) {
+                    // witness bookkeeping: furthest frontier reached in this shard
+                    const unsigned long long wc = *(volatile unsigned long long*)&*wit_cache;
+                    if ((int)(wc >> 32) != shard || (int)(uint32_t)wc < cgj) {
+                        *(volatile unsigned long long*)&*wit_cache =
+                            ((unsigned long long)(uint32_t)shard << 32) | (uint32_t)cgj;
+                        atomicMax(&p.shard_max_rank[shard], cgj);
+                    }
+                }
+            }
+        }
+        push(is_new != 0, cw, cbal);
+    }
+    // -- candidates: next member of each crashed-op class
+    for (int r = 0; r < cls_rounds && shard_alive && eager_t < 0; ++r) {
+        const int c = r * 32 + lane;
+        bool cand = c < ncls;
+        struct { int first, n, word, shift_width; } cr = {0, 0, 1, 0};
+        int4 cop = make_int4(OP_IMPOSSIBLE, 0, 0, 0);
+        if (cand) {
+            const int4* q = reinterpret_cast<const int4*>(p.classes + cls_base + c);
+            const int4 b = __ldg(q + 1);
+            cop = __ldg(q);
+            cr.first = b.x; cr.n = b.y; cr.word = b.z; cr.shift_width = b.w;
+        }
+        const int shift = cr.shift_width & 0xff, width = cr.shift_width >> 8;
+        uint64_t cw[KW];
+        uint64_t field = 0;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) { cw[i] = w[i]; if (i == cr.word) field = w[i]; }
+        const int count = (int)((field >> shift) & ((1ull << width) - 1));
+        cand = cand && count < cr.n;
+        if (cand) cand = __ldg(p.cls_inv_pos + cr.first + count) < fr_pos;
+        int32_t creg = preg;
+        int32_t cbal[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+        const bool ok = cand && model_step<MODEL>(cop, creg, cbal, nullptr, neg_ok != 0, w[1]);
+#pragma unroll
+        for (int i = 1; i < KW; ++i) if (i == cr.word) cw[i] += 1ull << shift;
+        cw[0] = KEY_VALID | ((uint64_t)(uint32_t)gj << 32) |
+                ((MODEL == JTB_MODEL_BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
+        int is_new = 0;
+        if (ok) {
+            int plen;
+            const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
+            my_probes++;
+            my_max_probe = max(my_max_probe, plen);
+            if (res < 0) {
+                atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
+                atomicCAS(&ctrl->stop, 0, 2);
+            }
+            is_new = res > 0;
+        }
+        push(is_new != 0, cw, cbal);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int KW>
 struct EntryLayout {
@@ -275,9 +444,6 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
     __shared__ CtaShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Ctrl* ctrl = p.ctrl;
-    const int cand_rounds = p.S_pad / 32;
-    const int cls_rounds = (p.max_nc + 31) / 32;
-    constexpr int SW = MODEL == JTB_MODEL_BANK ? 12 : MODEL == JTB_MODEL_SET ? 8 : 4;  // = slot_words(MODEL)
     const unsigned cap_mask = p.deque_cap - 1;
     const unsigned high = p.deque_cap / 2;   // donate the oldest entries beyond this; overflow goes to the ring
     uint64_t* const s_batch = s_deque + (size_t)p.deque_cap * EW;
@@ -475,17 +641,6 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
             if (!have) break;
             ++n_done;
             // ---------------- expand (warp-synchronous) ---------------------------------------------
-            const int gj = (int)((w[0] >> 32) & 0x3fffffffu);
-            const int32_t preg = (int32_t)(uint32_t)w[0];
-            const int32_t* row = p.rows + (size_t)gj * p.row_words;
-            const int32_t extra = __ldg(row + (lane & 15));
-            const int fr_pos = __shfl_sync(0xffffffffu, extra, 8);
-            const int shard = __shfl_sync(0xffffffffu, extra, 9);
-            const int gj_end = __shfl_sync(0xffffffffu, extra, 10);
-            const int cls_base = __shfl_sync(0xffffffffu, extra, 11);
-            const int ncls = __shfl_sync(0xffffffffu, extra, 12);
-            const int rslot = __shfl_sync(0xffffffffu, extra, 13);
-            const bool shard_alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
             int n_new_total = 0, n_new_local = 0;
             unsigned last_base = 0xffffffffu;   // deque index of the most recent local push
 
@@ -544,152 +699,8 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
                 }
                 n_new_total += n;
             };
-
-            // -- eager reads: a consistent read never changes the state, so if any candidate read is consistent
-            //    it is linearized immediately and exclusively (verdict- and witness-preserving: any path from
-            //    this config can be re-ordered to start with that read).  Not in Knossos; see DESIGN.md.
-            int eager_t = -1;
-            if (p.eager_reads && shard_alive) {
-                unsigned best_inv = 0xffffffffu;  // earliest-invoked consistent read seen by this lane
-                int best_t = -1;
-                for (int r = 0; r < cand_rounds; ++r) {
-                    const int t = r * 32 + lane;
-                    const int32_t* cell = row + ROW_EXTRA + t * SW;
-                    const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
-                    bool rd = op.x >= 0 && (op.x & 0xff) == JTB_F_READ && !((w[1] >> t) & 1ull);
-                    if (rd) {
-                        int32_t creg = preg;
-                        int32_t cbal[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                        rd = model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
-                    }
-                    if (rd && (unsigned)op.w < best_inv) { best_inv = (unsigned)op.w; best_t = t; }
-                }
-                const unsigned mn = __reduce_min_sync(0xffffffffu, best_inv);
-                if (mn != 0xffffffffu) {
-                    const unsigned who = __ballot_sync(0xffffffffu, best_inv == mn);
-                    eager_t = __shfl_sync(0xffffffffu, best_t, __ffs(who) - 1);
-                }
-            }
-            // -- candidates: ops in the open slots
-            for (int r = 0; r < cand_rounds && shard_alive; ++r) {
-                const int t = r * 32 + lane;
-                const int32_t* cell = row + ROW_EXTRA + t * SW;
-                const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
-                const bool cand = op.x >= 0 && !((w[1] >> t) & 1ull) && (eager_t < 0 || eager_t == t);
-                int32_t creg = preg;
-                int32_t cbal[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                bool ok = cand && model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
-                const bool is_front = t == rslot;
-                uint64_t cw[KW];
-#pragma unroll
-                for (int i = 0; i < KW; ++i) cw[i] = w[i];
-                int cgj = gj;
-                // frontier advance, warp-cooperative, for the child that linearizes the frontier op
-                const unsigned front_ok = __ballot_sync(0xffffffffu, ok && is_front);
-                if (front_ok) {
-                    uint64_t m = w[1];
-                    int adv = 0;
-                    const int32_t* rw = row;
-                    int32_t ex = extra;
-                    for (;;) {
-                        const int32_t word = __shfl_sync(0xffffffffu, ex, lane >> 2);
-                        const int sl = (word >> (8 * (lane & 3))) & 0xff;
-                        const bool setb = sl != 0xff && ((m >> sl) & 1ull);
-                        const unsigned peers = __match_any_sync(0xffffffffu, sl);
-                        const bool pass = setb && (peers & ((1u << lane) - 1)) == 0;
-                        const unsigned pm = __ballot_sync(0xffffffffu, pass);
-                        const int n = pm == 0xffffffffu ? 32 : __ffs(~pm) - 1;
-                        const uint64_t clr = (lane < n) ? (1ull << sl) : 0ull;
-                        const uint32_t clo = __reduce_or_sync(0xffffffffu, (uint32_t)clr);
-                        const uint32_t chi = __reduce_or_sync(0xffffffffu, (uint32_t)(clr >> 32));
-                        m &= ~((uint64_t)clo | ((uint64_t)chi << 32));
-                        adv += n;
-                        if (n < 32) break;
-                        rw += (size_t)32 * p.row_words;
-                        ex = __ldg(rw + (lane & 15));
-                    }
-                    if (is_front) { cgj = gj + 1 + adv; cw[1] = m; }
-                }
-                if (ok && !is_front) cw[1] |= 1ull << t;
-                cw[0] = KEY_VALID | ((uint64_t)(uint32_t)cgj << 32) |
-                        ((MODEL == JTB_MODEL_BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
-                int is_new = 0;
-                if (ok) {
-                    if (cgj >= gj_end) {
-                        // every :ok op of the shard is linearized -> VALID
-                        if (atomicExch(&p.shard_found[shard], 1) == 0) {
-                            if (atomicSub(&ctrl->n_undecided, 1) == 1) atomicCAS(&ctrl->stop, 0, 1);
-                        }
-                    } else {
-                        int plen;
-                        const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
-                        my_probes++;
-                        my_max_probe = max(my_max_probe, plen);
-                        if (res < 0) {
-                            atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
-                            atomicCAS(&ctrl->stop, 0, 2);
-                        }
-                        is_new = res > 0;
-                        if (is_new && cgj > gj) {
-                            // witness bookkeeping: furthest frontier reached in this shard
-                            const unsigned long long wc = *(volatile unsigned long long*)&sh.wit_cache;
-                            if ((int)(wc >> 32) != shard || (int)(uint32_t)wc < cgj) {
-                                *(volatile unsigned long long*)&sh.wit_cache =
-                                    ((unsigned long long)(uint32_t)shard << 32) | (uint32_t)cgj;
-                                atomicMax(&p.shard_max_rank[shard], cgj);
-                            }
-                        }
-                    }
-                }
-                push_children(is_new != 0, cw, cbal);
-            }
-            // -- candidates: next member of each crashed-op class
-            for (int r = 0; r < cls_rounds && shard_alive && eager_t < 0; ++r) {
-                const int c = r * 32 + lane;
-                bool cand = c < ncls;
-                struct { int first, n, word, shift_width; } cr = {0, 0, 1, 0};
-                int4 cop = make_int4(OP_IMPOSSIBLE, 0, 0, 0);
-                if (cand) {
-                    const int4* q = reinterpret_cast<const int4*>(p.classes + cls_base + c);
-                    const int4 b = __ldg(q + 1);
-                    cop = __ldg(q);
-                    cr.first = b.x; cr.n = b.y; cr.word = b.z; cr.shift_width = b.w;
-                }
-                const int shift = cr.shift_width & 0xff, width = cr.shift_width >> 8;
-                uint64_t cw[KW];
-                uint64_t field = 0;
-#pragma unroll
-                for (int i = 0; i < KW; ++i) { cw[i] = w[i]; if (i == cr.word) field = w[i]; }
-                const int count = (int)((field >> shift) & ((1ull << width) - 1));
-                cand = cand && count < cr.n;
-                if (cand) cand = __ldg(p.cls_inv_pos + cr.first + count) < fr_pos;
-                int32_t creg = preg;
-                int32_t cbal[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                const bool ok = cand && model_step<MODEL>(cop, creg, cbal, nullptr, neg_ok != 0, w[1]);
-#pragma unroll
-                for (int i = 1; i < KW; ++i) if (i == cr.word) cw[i] += 1ull << shift;
-                cw[0] = KEY_VALID | ((uint64_t)(uint32_t)gj << 32) |
-                        ((MODEL == JTB_MODEL_BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
-                int is_new = 0;
-                if (ok) {
-                    int plen;
-                    const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
-                    my_probes++;
-                    my_max_probe = max(my_max_probe, plen);
-                    if (res < 0) {
-                        atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
-                        atomicCAS(&ctrl->stop, 0, 2);
-                    }
-                    is_new = res > 0;
-                }
-                push_children(is_new != 0, cw, cbal);
-            }
+            expand_config<MODEL, KW>(p, ctrl, neg_ok, w, pbal, lane, cas_first, &sh.wit_cache, my_probes, my_max_probe,
+                                     push_children);
             if (lane == 0) {
                 if (n_new_local) atomicAdd(&sh.n_new, (unsigned)n_new_local);
                 my_expansions++;
