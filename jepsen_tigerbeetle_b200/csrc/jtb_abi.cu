@@ -248,7 +248,8 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         size_t max_table = ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)64 << 30;
         max_table = std::min(max_table, ctx->table.cap + (free_b > reserve ? free_b - reserve : 0));
         // start at 1 GiB, or at 4x what the previous call on this context ended up needing (warm context)
-        size_t start_bytes = std::max<size_t>((size_t)1 << 30, (size_t)ctx->last_configs * 4 * KW * 8);
+        const size_t min_start = getenv("JTB_TABLE_START_MB") ? (size_t)atoll(getenv("JTB_TABLE_START_MB")) << 20 : (size_t)1 << 30;
+        size_t start_bytes = std::max<size_t>(min_start, (size_t)ctx->last_configs * 4 * KW * 8);
         size_t table_bytes = std::min<size_t>(max_table, ctx->opts.table_bytes ? ctx->opts.table_bytes : start_bytes);
         uint64_t n_slots = 1;
         while (n_slots * 2 * KW * 8 <= table_bytes) n_slots <<= 1;

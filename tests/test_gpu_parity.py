@@ -267,3 +267,27 @@ def test_wide_keys_many_crashed_op_classes(gpu_ctx, oracle_mod, n_clients, n_ops
     same_verdict(g, o)
     assert g["valid"] == H.INVALID and g["shards"][0]["witness_index"] == int(h.index[reads[3]])
     assert g["configs"] == o["configs"]
+
+
+def test_time_budget_and_edge_histories(gpu_ctx):
+    from jepsen_tigerbeetle_b200 import native
+    m = model_for("bank")
+    h = synth.generate(synth.SynthSpec("bank", 10000, 32, 1, tau_think_ns=2e6, stale_read=True))
+    with native.Context(time_budget_ms=5, eager_reads=False) as ctx:      # 5 ms is far too little for this search
+        g = ctx.check_linearizable(h, m)
+    assert g["valid"] == H.UNKNOWN and g["shards"][0]["cause"] == 2 and g["shards"][0]["witness_index"] == -1
+    # a history with no completed op at all (every op crashed) is trivially linearizable
+    ops = kat.ops("0:inv write 1, 1:inv write 2, 0:info write 1")
+    g = gpu_ctx.check_linearizable(H.flatten_ops(ops, "cas-register"), model_for("cas-register"))
+    assert g["valid"] == H.VALID and g["configs"] == 0
+    # only nemesis ops
+    g = gpu_ctx.check_linearizable(H.flatten_ops([{"type": "info", "f": "kill", "process": "nemesis", "value": None}],
+                                                 "cas-register"), model_for("cas-register"))
+    assert g["valid"] == H.VALID
+    # malformed: completion without invocation -> error, which the Checker mirror turns into :unknown
+    bad = H.flatten_ops(kat.ops("0:ok write 1"), "cas-register")
+    with pytest.raises(native.NativeError):
+        gpu_ctx.check_linearizable(bad, model_for("cas-register"))
+    from jepsen_tigerbeetle_b200 import checker as ck
+    r = ck.check_safe(ck.linearizable({"model": "cas-register"}, ctx=gpu_ctx), {}, bad)
+    assert r["valid?"] == "unknown" and "completion without invocation" in r["error"]
