@@ -291,3 +291,24 @@ def test_time_budget_and_edge_histories(gpu_ctx):
     from jepsen_tigerbeetle_b200 import checker as ck
     r = ck.check_safe(ck.linearizable({"model": "cas-register"}, ctx=gpu_ctx), {}, bad)
     assert r["valid?"] == "unknown" and "completion without invocation" in r["error"]
+
+
+@pytest.mark.parametrize("model", ["register", "cas-register", "set", "bank"])
+def test_arbitrary_small_histories(gpu_ctx, oracle_mod, model):
+    """300 arbitrary (mostly non-linearizable) small histories per model: verdict, witness and — when the search
+    is exhaustive — the configuration count must equal the oracle's (which agrees with brute force on these)."""
+    import arbitrary
+    rng = np.random.default_rng(20260922)
+    m = H.make_model(H.MODEL_BANK, accounts=[1, 2, 3]) if model == "bank" else model_for(model)
+    n_invalid = 0
+    for _ in range(300):
+        ops = arbitrary.arbitrary_history(model, rng)
+        h = H.flatten_ops(ops, model)
+        g = gpu_ctx.check_linearizable(h, m)
+        o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
+        same_verdict(g, o)
+        if o["valid"] == H.INVALID:
+            n_invalid += 1
+            assert g["configs"] == o["configs"], ops
+            assert oracle_mod.check_linearizable(h, m, 0)["shards"][0]["witness_index"] == g["shards"][0]["witness_index"]
+    assert n_invalid > 30
