@@ -82,8 +82,8 @@ int launch_wgl_b(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t 
 
 template <int MODEL, int KW>
 int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem, int ctas_per_sm) {
-    return ctas_per_sm >= 4 ? launch_wgl_b<MODEL, KW, 4>(ctx, p, neg_ok, grid, smem)
-                            : launch_wgl_b<MODEL, KW, 3>(ctx, p, neg_ok, grid, smem);
+    return ctas_per_sm >= JTB_CTAS_EXACT ? launch_wgl_b<MODEL, KW, JTB_CTAS_EXACT>(ctx, p, neg_ok, grid, smem)
+                                         : launch_wgl_b<MODEL, KW, JTB_CTAS_EAGER>(ctx, p, neg_ok, grid, smem);
 }
 
 template <int MODEL>
@@ -230,7 +230,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         const size_t smem = (size_t)(deque_cap + WGL_BATCH) * EW * 8;   // deque + staged batch
         // eager-read searches are small and latency-bound: 3 CTAs/SM (no register spills) wins; the
         // Knossos-exact space is throughput-bound: 4 CTAs/SM (measured A/B)
-        const int want_ctas = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? 4 : 3;
+        const int want_ctas = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? JTB_CTAS_EXACT : JTB_CTAS_EAGER;
         int ctas_per_sm = (int)std::min<size_t>(want_ctas, (220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, ctas_per_sm);
         const int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;

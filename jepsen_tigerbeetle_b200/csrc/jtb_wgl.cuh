@@ -408,7 +408,16 @@ struct EntryLayout {
     static constexpr int EW = KW + (HAS_BAL ? 4 : 0);  // 64-bit words per ring entry
 };
 
-constexpr int WGL_WARPS = 8;
+#ifndef JTB_WARPS
+#define JTB_WARPS 8
+#endif
+#ifndef JTB_CTAS_EXACT
+#define JTB_CTAS_EXACT 4   // resident CTAs/SM for the Knossos-exact space (throughput-bound)
+#endif
+#ifndef JTB_CTAS_EAGER
+#define JTB_CTAS_EAGER 3   // resident CTAs/SM for eager-read searches (latency-bound)
+#endif
+constexpr int WGL_WARPS = JTB_WARPS;
 constexpr int WGL_THREADS = WGL_WARPS * 32;
 constexpr unsigned WGL_MAX_DONATE = 64;       // per step, when donating to hungry warps
 #ifndef JTB_BATCH
