@@ -238,6 +238,8 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         // work ring
         uint64_t ring_entries = 1ull << 22;
         while (ring_entries < 4 * per_step_push + 2 * searchable.size()) ring_entries <<= 1;
+        // test hook: start with a ring that is too small so that the RING_FULL pause/grow/resume path runs
+        const bool tiny_ring = getenv("JTB_TEST_TINY_RING") != nullptr;
         if (ensure(ctx, ctx->pool, ring_entries * EW * 8)) return -1;
         CK(cudaMemsetAsync(ctx->pool.p, 0, ring_entries * EW * 8, ctx->stream));
         CK(cudaMemcpyAsync(ctx->pool.p, init_entries.data(), init_entries.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -276,7 +278,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.slot_mask = n_slots - 1;
             p.ring = (uint64_t*)ctx->pool.p;
             p.ring_mask = ring_entries - 1;
-            p.ring_guard = ring_entries - 3 * per_step_push;
+            p.ring_guard = (tiny_ring && attempts == 1) ? 20000 : ring_entries - 3 * per_step_push;
             p.ctrl = (Ctrl*)ctx->ctrl.p;
             p.shard_found = (int*)ctx->found.p;
             p.shard_max_rank = (int*)ctx->maxrank.p;
