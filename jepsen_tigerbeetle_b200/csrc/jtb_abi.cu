@@ -71,19 +71,22 @@ int upload(jtb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
     return 0;
 }
 
-template <int MODEL, int KW, int MINB>
+template <int MODEL, int KW, int MINB, bool EAGER>
 int launch_wgl_b(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem) {
-    auto k = wgl_search_kernel<MODEL, KW, MINB>;
+    auto k = wgl_search_kernel<MODEL, KW, MINB, EAGER>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, WGL_THREADS, smem, ctx->stream>>>(p, neg_ok);
     CK(cudaGetLastError());
     return 0;
 }
 
+// two builds of the kernel: Knossos-exact space (no eager-read code, 64 regs, JTB_CTAS_EXACT CTAs/SM) and the
+// eager-read default (78 regs, no spills, JTB_CTAS_EAGER CTAs/SM)
 template <int MODEL, int KW>
 int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem, int ctas_per_sm) {
-    return ctas_per_sm >= JTB_CTAS_EXACT ? launch_wgl_b<MODEL, KW, JTB_CTAS_EXACT>(ctx, p, neg_ok, grid, smem)
-                                         : launch_wgl_b<MODEL, KW, JTB_CTAS_EAGER>(ctx, p, neg_ok, grid, smem);
+    (void)ctas_per_sm;
+    return p.eager_reads ? launch_wgl_b<MODEL, KW, JTB_CTAS_EAGER, true>(ctx, p, neg_ok, grid, smem)
+                         : launch_wgl_b<MODEL, KW, JTB_CTAS_EXACT, false>(ctx, p, neg_ok, grid, smem);
 }
 
 template <int MODEL>

@@ -235,7 +235,7 @@ __device__ __forceinline__ bool model_step(const int4 op, int32_t& reg, int32_t 
 // One expansion, warp-synchronous: evaluates every candidate of the configuration (w, pbal), probes/inserts the
 // consistent children and hands the NEW ones to `push(is_new, key words, balances)` (called by all lanes, once per
 // candidate round).  Shared by the search kernels; `wit_cache` is a shared-memory filter for the witness atomicMax.
-template <int MODEL, int KW, typename Push>
+template <int MODEL, int KW, bool EAGER, typename Push>
 __device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, const int neg_ok, const uint64_t (&w)[KW],
                                               const int32_t (&pbal)[8], const int lane, const bool cas_first,
                                               unsigned long long* wit_cache, unsigned long long& my_probes,
@@ -258,7 +258,7 @@ __device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, co
     //    it is linearized immediately and exclusively (verdict- and witness-preserving: any path from
     //    this config can be re-ordered to start with that read).  Not in Knossos; see DESIGN.md.
     int eager_t = -1;
-    if (p.eager_reads && shard_alive) {
+    if (EAGER && shard_alive) {
         unsigned best_inv = 0xffffffffu;  // earliest-invoked consistent read seen by this lane
         int best_t = -1;
         for (int r = 0; r < cand_rounds; ++r) {
@@ -445,7 +445,7 @@ __device__ __forceinline__ uint64_t ld_volatile64(const uint64_t* p) { return *(
 
 // MINB = resident CTAs per SM the register budget is cut for: 4 (64 regs, 32 warps/SM) is best for large,
 // throughput-bound searches; 3 (78 regs, no spills) is 11-17 % faster on small latency-bound ones (measured A/B).
-template <int MODEL, int KW, int MINB>
+template <int MODEL, int KW, int MINB, bool EAGER>
 __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const WglParams p, const int neg_ok) {
     using L = EntryLayout<MODEL, KW>;
     constexpr int EW = L::EW;
@@ -708,8 +708,8 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
                 }
                 n_new_total += n;
             };
-            expand_config<MODEL, KW>(p, ctrl, neg_ok, w, pbal, lane, cas_first, &sh.wit_cache, my_probes, my_max_probe,
-                                     push_children);
+            expand_config<MODEL, KW, EAGER>(p, ctrl, neg_ok, w, pbal, lane, cas_first, &sh.wit_cache, my_probes,
+                                            my_max_probe, push_children);
             if (lane == 0) {
                 if (n_new_local) atomicAdd(&sh.n_new, (unsigned)n_new_local);
                 my_expansions++;
