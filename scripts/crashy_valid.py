@@ -1,0 +1,18 @@
+"""The three crash-heavy VALID histories the soak test found (GPU :unknown vs CPU valid) + a few more."""
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jepsen_tigerbeetle_b200 import native, synth, history as H
+import oracle
+specs = [synth.SynthSpec('cas-register', 2500, 24, 809007372, p_info=0.3, tau_think_ns=20e6, n_values=30),
+         synth.SynthSpec('register', 1000, 24, 902980068, p_info=0.3, tau_think_ns=5e6, n_values=30, stale_read=True),
+         synth.SynthSpec('register', 2500, 40, 321354213, p_info=0.1, tau_think_ns=20e6, n_values=30, stale_by=3),
+         synth.SynthSpec('cas-register', 1000, 16, 1, p_info=0.05), synth.SynthSpec('cas-register', 50000, 2048, 1, p_info=0.3, n_keys=256, grouped_keys=True),
+         synth.SynthSpec('cas-register', 50000, 64, 1, p_info=0.3, n_keys=8, grouped_keys=True)]
+M = {"register": H.MODEL_REGISTER, "cas-register": H.MODEL_CAS_REGISTER}
+with native.Context(max_configs=400_000_000) as ctx:
+    for sp in specs:
+        h = synth.generate(sp)
+        m = H.make_model(M[sp.model])
+        t = time.perf_counter(); o = oracle.check_linearizable(h, m, 3, eager_reads=True, n_threads=8, max_configs=5_000_000); tc = time.perf_counter() - t
+        g = ctx.check_linearizable(h, m)
+        print(sp.model, sp.n_ops, sp.n_clients, sp.p_info, "keys", sp.n_keys, "| gpu", g["valid"], g["configs"], round(g["seconds_total"] * 1e3, 1), "ms | cpu", o["valid"], o["configs"], round(tc * 1e3, 1), "ms", flush=True)
