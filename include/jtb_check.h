@@ -106,6 +106,11 @@ typedef struct jtb_model {
  * of configurations drops by an order of magnitude).  Knossos does not do this; set this flag to visit
  * exactly the configurations Knossos' WGL would. */
 #define JTB_OPT_NO_EAGER_READS 1
+/* For histories with crashed (:info) ops a few depth-first "scout" warps walk the same configuration space in
+ * knossos.wgl's order (and three other orders) beside the exhaustive search, each with a private visited table;
+ * a scout can only ever report VALID (it found a linearization), so verdicts, witnesses and exhaustive
+ * configuration counts are unaffected.  Set this flag to run the exhaustive search alone. */
+#define JTB_OPT_NO_SCOUTS 2
 
 /* Options for a context.  Zero-initialise, then set what you need. */
 typedef struct jtb_opts {
@@ -241,7 +246,8 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
 /* ---- diagnostics: counters of the last jtb_check_linearizable call ------------------------------ *
  * out[0..11] = configs, probes, expansions, ring tail, ring head, idle polls, max probe length,
  * table slots, grid CTAs, ring entries, search launches (pause/resume growth + 1), kernel microseconds,
- * out[12..14] = host->device bytes, device->host bytes, CUDA kernels launched */
+ * out[12..14] = host->device bytes, device->host bytes, CUDA kernels launched,
+ * out[15..18] = scout steps, scout configs, shards decided by a scout, scouts launched */
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n);
 
 /* ---- diagnostics: host preparation only (pairing, slots, tables) — no device work; returns seconds

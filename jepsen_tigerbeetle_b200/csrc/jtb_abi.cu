@@ -7,9 +7,11 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "jtb_wgl.cuh"
+#include "jtb_scout.cuh"
 #include "jtb_scans.cuh"
 #include "jtb_table_bench.cuh"
 
@@ -24,16 +26,15 @@ struct jtb_ctx {
     int device = 0;
     jtb_opts opts{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t scout_stream = nullptr;   // the depth-first scouts run beside the search kernel
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_setup = nullptr;
     int n_sms = 0;
     std::string err;
     std::mutex mu;  // a context serialises its calls; use one context per JVM thread for concurrency
     // cached device buffers (grown on demand, reused across calls)
-    DevBuf table, pool, rows, ops, read_bal, set_need, classes, cls_inv, ctrl, found, maxrank, scratch[8];
-    // pinned staging
-    void* pin = nullptr;
-    size_t pin_cap = 0;
-    unsigned long long stats[16] = {0};
+    DevBuf table, pool, rows, classes, cls_inv, ctrl, found, maxrank;
+    DevBuf sc_init, sc_tables, sc_stacks, sc_ctl;   // scouts: initial entries, private tables, stacks, control words
+    unsigned long long stats[20] = {0};
     unsigned long long last_configs = 0;  // configs of the previous search (sizes the next table)
 };
 
@@ -100,6 +101,72 @@ int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid
     return -1;
 }
 
+// Stops the scouts on every way out of a search (they only end on their own when their budget is spent).
+struct ScoutGuard {
+    jtb_ctx* ctx;
+    bool active = false;
+    explicit ScoutGuard(jtb_ctx* c) : ctx(c) {}
+    int stop() {
+        if (!active) return 0;
+        active = false;
+        static const unsigned long long one = 1;
+        // an 8-byte pageable copy is staged at once; ctx->stream never waits for the scout stream
+        cudaError_t e = cudaMemcpyAsync((unsigned long long*)ctx->sc_ctl.p + 1, &one, 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->scout_stream);
+        if (e != cudaSuccess) { ctx->err = std::string("stopping the scouts: ") + cudaGetErrorString(e); return -1; }
+        return 0;
+    }
+    ~ScoutGuard() { stop(); }
+};
+
+// CUDA loads kernels lazily, and loading one synchronizes the context: the first launch of a search / compact /
+// re-hash kernel would wait for the running scouts (measured: the search sat behind them for 16 s).  So every kernel
+// a search can need is loaded before the scouts start.
+template <typename K>
+int preload(jtb_ctx* ctx, K kernel) {
+    cudaFuncAttributes a;
+    CK(cudaFuncGetAttributes(&a, kernel));
+    return 0;
+}
+
+template <int MODEL, int KW>
+int preload_search(jtb_ctx* ctx, bool eager) {
+    constexpr int EW = KW + (MODEL == JTB_MODEL_BANK ? 4 : 0);
+    int rc = eager ? (preload(ctx, wgl_search_kernel<MODEL, KW, JTB_CTAS_EAGER, true>) | preload(ctx, wgl_scout_kernel<MODEL, KW, true>))
+                   : (preload(ctx, wgl_search_kernel<MODEL, KW, JTB_CTAS_EXACT, false>) | preload(ctx, wgl_scout_kernel<MODEL, KW, false>));
+    rc |= preload(ctx, table_rehash_kernel<KW>) | preload(ctx, ring_compact_kernel<EW>) | preload(ctx, wgl_resume_ctrl_kernel);
+    return rc ? -1 : 0;
+}
+
+template <int MODEL>
+int preload_search_kw(jtb_ctx* ctx, int kw, bool eager) {
+    switch (kw) {
+    case 2: return preload_search<MODEL, 2>(ctx, eager);
+    case 4: return preload_search<MODEL, 4>(ctx, eager);
+    case 8: return preload_search<MODEL, 8>(ctx, eager);
+    }
+    return -1;
+}
+
+template <int MODEL, int KW>
+int launch_scout(jtb_ctx* ctx, const WglParams& p, const ScoutParams& sp, int neg_ok, int n_scouts) {
+    if (p.eager_reads) wgl_scout_kernel<MODEL, KW, true><<<n_scouts, 32, 0, ctx->scout_stream>>>(p, sp, neg_ok);
+    else wgl_scout_kernel<MODEL, KW, false><<<n_scouts, 32, 0, ctx->scout_stream>>>(p, sp, neg_ok);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int MODEL>
+int launch_scout_kw(jtb_ctx* ctx, int kw, const WglParams& p, const ScoutParams& sp, int neg_ok, int n_scouts) {
+    switch (kw) {
+    case 2: return launch_scout<MODEL, 2>(ctx, p, sp, neg_ok, n_scouts);
+    case 4: return launch_scout<MODEL, 4>(ctx, p, sp, neg_ok, n_scouts);
+    case 8: return launch_scout<MODEL, 8>(ctx, p, sp, neg_ok, n_scouts);
+    }
+    ctx->err = "unsupported key width";
+    return -1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -139,8 +206,12 @@ jtb_ctx* jtb_create(const jtb_opts* opts) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, ctx->device);
     ctx->n_sms = prop.multiProcessorCount;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->scout_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_setup, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return nullptr;
     }
@@ -150,15 +221,14 @@ jtb_ctx* jtb_create(const jtb_opts* opts) {
 void jtb_destroy(jtb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->table, &ctx->pool, &ctx->rows, &ctx->ops, &ctx->read_bal, &ctx->set_need, &ctx->classes,
-                      &ctx->cls_inv, &ctx->ctrl, &ctx->found, &ctx->maxrank};
+    DevBuf* bufs[] = {&ctx->table, &ctx->pool, &ctx->rows, &ctx->classes, &ctx->cls_inv, &ctx->ctrl, &ctx->found,
+                      &ctx->maxrank, &ctx->sc_init, &ctx->sc_tables, &ctx->sc_stacks, &ctx->sc_ctl};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
-    for (DevBuf& b : ctx->scratch)
-        if (b.p) cudaFree(b.p);
-    if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_setup) cudaEventDestroy(ctx->ev_setup);
+    if (ctx->scout_stream) cudaStreamDestroy(ctx->scout_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -215,6 +285,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     uint64_t configs = 0, probes = 0;
     ctx->stats[10] = 0;
     ctx->stats[12] = ctx->stats[13] = ctx->stats[14] = 0;
+    ctx->stats[15] = ctx->stats[16] = ctx->stats[17] = ctx->stats[18] = 0;
     Ctrl hc;
     std::memset(&hc, 0, sizeof hc);
     std::vector<int> h_found(n_shards, 0), h_max(n_shards, 0);
@@ -268,27 +339,99 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         for (int s = 0; s < n_shards; ++s) h_max[s] = (int)P.rank_base[s];
         CK(cudaMemcpyAsync(ctx->maxrank.p, h_max.data(), n_shards * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         DevBuf ring2, table2;  // growth targets (freed below)
-        auto free_tmp = [&]() { if (ring2.p) cudaFree(ring2.p); if (table2.p) cudaFree(table2.p); ring2 = DevBuf(); table2 = DevBuf(); };
+        // cudaFree synchronizes the whole device, i.e. it would wait for the scouts: while they run, frees are deferred
+        // (cudaFree is valid for stream-ordered allocations too)
+        ScoutGuard scouts(ctx);
+        std::vector<void*> deferred;
+        auto free_tmp = [&]() {
+            scouts.stop();
+            for (void* q : deferred) cudaFree(q);
+            deferred.clear();
+            if (ring2.p) cudaFree(ring2.p);
+            if (table2.p) cudaFree(table2.p);
+            ring2 = DevBuf(); table2 = DevBuf();
+        };
+        auto grow_buf = [&](DevBuf& b, size_t bytes) -> int {
+            if (bytes <= b.cap) return 0;
+            if (b.p) { if (scouts.active) deferred.push_back(b.p); else cudaFree(b.p); }
+            b = DevBuf();
+            // cudaMalloc also synchronizes with running kernels (measured: the search sat behind the scouts for 16 s at
+            // its first table growth); the stream-ordered allocator does not
+            const cudaError_t e = scouts.active ? cudaMallocAsync(&b.p, bytes, ctx->stream) : cudaMalloc(&b.p, bytes);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                b.p = nullptr;
+                if (scouts.stop()) return -1;   // out of memory with frees pending: give the scouts up
+                for (void* q : deferred) cudaFree(q);
+                deferred.clear();
+                CK(cudaMalloc(&b.p, bytes));
+            }
+            b.cap = bytes;
+            return 0;
+        };
         int attempts = 0;
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        WglParams pb{};   // what the search kernel and the scouts share
+        pb.rows = (const int32_t*)ctx->rows.p;
+        pb.classes = (const ClassRec*)ctx->classes.p;
+        pb.cls_inv_pos = (const int32_t*)ctx->cls_inv.p;
+        pb.ctrl = (Ctrl*)ctx->ctrl.p;
+        pb.shard_found = (int*)ctx->found.p;
+        pb.shard_max_rank = (int*)ctx->maxrank.p;
+        pb.row_words = P.row_words;
+        pb.S_pad = P.S_pad;
+        pb.n_shards = n_shards;
+        pb.max_nc = P.max_nc;
+        pb.eager_reads = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? 0 : 1;
+        // ---- depth-first scouts (jtb_scout.cuh): only where the crowd is known to drown — histories with
+        //      crashed ops — and launched FIRST so that they are resident before the persistent CTAs fill the SMs
+        int64_t max_shard_events = 0;
+        for (int s : searchable) max_shard_events = std::max<int64_t>(max_shard_events, h->shard_off[s + 1] - h->shard_off[s]);
+        int n_scouts = 0;
+        const bool scout_only = getenv("JTB_SCOUT_ONLY") != nullptr;   // test hook: no search kernel at all
+        if (!(ctx->opts.flags & JTB_OPT_NO_SCOUTS) && !getenv("JTB_NO_SCOUTS") && (P.max_nc > 0 || scout_only) &&
+            max_shard_events < (1ll << 29)) {
+            n_scouts = getenv("JTB_SCOUTS") ? std::max(1, atoi(getenv("JTB_SCOUTS"))) : SCOUT_ORDERS;
+            ScoutParams sp{};
+            sp.n_init = (int)searchable.size();
+            sp.n_orders = getenv("JTB_SCOUT_ORDERS") ? std::min(SCOUT_ORDERS, std::max(1, atoi(getenv("JTB_SCOUT_ORDERS")))) : SCOUT_ORDERS;
+            const uint64_t sc_slots = 1ull << 22;                       // 2 M configs per scout
+            sp.slot_mask = sc_slots - 1;
+            sp.stack_cap = (uint32_t)(max_shard_events + 2);            // a path linearizes each op at most once
+            sp.pair_budget = 8ull << 20;
+            if (upload(ctx, ctx->sc_init, init_entries) ||
+                ensure(ctx, ctx->sc_tables, (size_t)n_scouts * sc_slots * KW * 8) ||
+                ensure(ctx, ctx->sc_stacks, (size_t)n_scouts * sp.stack_cap * (EW + 1) * 8) ||
+                ensure(ctx, ctx->sc_ctl, SCOUT_CTL_WORDS * 8))
+                return -1;
+            CK(cudaMemsetAsync(ctx->sc_tables.p, 0, (size_t)n_scouts * sc_slots * KW * 8, ctx->stream));
+            CK(cudaMemsetAsync(ctx->sc_ctl.p, 0, SCOUT_CTL_WORDS * 8, ctx->stream));
+            sp.init = (const uint64_t*)ctx->sc_init.p;
+            sp.tables = (uint64_t*)ctx->sc_tables.p;
+            sp.stacks = (uint64_t*)ctx->sc_stacks.p;
+            sp.ctl = (unsigned long long*)ctx->sc_ctl.p;
+            CK(cudaEventRecord(ctx->ev_setup, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->scout_stream, ctx->ev_setup, 0));
+            int rc;
+            if (m->kind == JTB_MODEL_BANK) rc = preload_search_kw<JTB_MODEL_BANK>(ctx, KW, pb.eager_reads != 0);
+            else if (m->kind == JTB_MODEL_SET) rc = preload_search<JTB_MODEL_SET, 2>(ctx, pb.eager_reads != 0);
+            else rc = preload_search_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, pb.eager_reads != 0);
+            if (rc) return rc;
+            if (m->kind == JTB_MODEL_BANK) rc = launch_scout_kw<JTB_MODEL_BANK>(ctx, KW, pb, sp, m->negative_balances_ok, n_scouts);
+            else if (m->kind == JTB_MODEL_SET) rc = launch_scout<JTB_MODEL_SET, 2>(ctx, pb, sp, 0, n_scouts);
+            else rc = launch_scout_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, pb, sp, 0, n_scouts);
+            if (rc) return rc;
+            scouts.active = true;
+        }
         for (;;) {
             ++attempts;
-            WglParams p{};
-            p.rows = (const int32_t*)ctx->rows.p;
-            p.classes = (const ClassRec*)ctx->classes.p;
-            p.cls_inv_pos = (const int32_t*)ctx->cls_inv.p;
+            if (scout_only) { hc.stop = 2; hc.cause = JTB_CAUSE_BUDGET; break; }
+            WglParams p = pb;
             p.table = (uint64_t*)ctx->table.p;
             p.slot_mask = n_slots - 1;
             p.ring = (uint64_t*)ctx->pool.p;
             p.ring_mask = ring_entries - 1;
             p.ring_guard = (tiny_ring && attempts == 1) ? 20000 : ring_entries - 3 * per_step_push;
-            p.ctrl = (Ctrl*)ctx->ctrl.p;
-            p.shard_found = (int*)ctx->found.p;
-            p.shard_max_rank = (int*)ctx->maxrank.p;
-            p.row_words = P.row_words;
-            p.S_pad = P.S_pad;
-            p.n_shards = n_shards;
-            p.max_nc = P.max_nc;
             const uint64_t load_guard = (uint64_t)(0.50 * (double)n_slots);  // linear probing: keep chains short
             p.max_configs = load_guard;
             p.budget_cause = JTB_CAUSE_TABLE_FULL;
@@ -299,9 +442,6 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.time_budget_ns = (unsigned long long)ctx->opts.time_budget_ms * 1000000ull;
             p.deque_cap = deque_cap;
             p.cas_first = getenv("JTB_CAS_FIRST") ? atoi(getenv("JTB_CAS_FIRST")) : 0;
-            p.eager_reads = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? 0 : 1;
-            p.max_chain = getenv("JTB_CHAIN") ? atoi(getenv("JTB_CHAIN")) : 0;
-            p.narrow_cas = getenv("JTB_NARROW_CAS") ? atoi(getenv("JTB_NARROW_CAS")) : 0;
             int rc;
             if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem, ctas_per_sm);
             else if (m->kind == JTB_MODEL_SET) rc = launch_wgl<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem, ctas_per_sm);
@@ -312,9 +452,10 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             const bool grow_table = hc.stop == 2 && hc.cause == JTB_CAUSE_TABLE_FULL && n_slots * KW * 8 * 4 <= max_table;
             const bool grow_ring = hc.stop == 2 && hc.cause == CAUSE_RING_FULL && ring_entries * EW * 8 * 4 <= ((size_t)16 << 30);
             if (!grow_table && !grow_ring) break;
+            if (hc.n_undecided <= 0) break;   // the scouts decided every shard while the search was pausing
             // ---- pause/resume: the live work is exactly the non-zero ring slots ---------------------
             const uint64_t new_ring_entries = grow_ring ? ring_entries * 4 : ring_entries;
-            if (ensure(ctx, ring2, new_ring_entries * EW * 8)) { free_tmp(); return -1; }
+            if (grow_buf(ring2, new_ring_entries * EW * 8)) { free_tmp(); return -1; }
             CK(cudaMemsetAsync(ring2.p, 0, new_ring_entries * EW * 8, ctx->stream));
             Ctrl* dc = (Ctrl*)ctx->ctrl.p;
             CK(cudaMemsetAsync(&dc->tail, 0, sizeof(unsigned long long), ctx->stream));
@@ -327,10 +468,11 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             std::swap(ctx->pool, ring2);
             ring_entries = new_ring_entries;
             CK(cudaMemsetAsync(&dc->head, 0, sizeof(unsigned long long), ctx->stream));
-            CK(cudaMemsetAsync(&dc->stop, 0, 2 * sizeof(int), ctx->stream));  // stop, cause
+            wgl_resume_ctrl_kernel<<<1, 1, 0, ctx->stream>>>(dc);   // stop, cause := 0 (unless everything is decided)
+            CK(cudaGetLastError());
             if (grow_table) {
                 const uint64_t new_slots = n_slots * 4;
-                if (ensure(ctx, table2, new_slots * KW * 8)) { free_tmp(); return -1; }
+                if (grow_buf(table2, new_slots * KW * 8)) { free_tmp(); return -1; }
                 CK(cudaMemsetAsync(table2.p, 0, new_slots * KW * 8, ctx->stream));
                 if (KW == 2) table_rehash_kernel<2><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
                 else if (KW == 4) table_rehash_kernel<4><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
@@ -338,9 +480,27 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
                 CK(cudaGetLastError());
                 CK(cudaStreamSynchronize(ctx->stream));
                 std::swap(ctx->table, table2);
-                if (table2.p) { cudaFree(table2.p); table2 = DevBuf(); }  // release the old table right away
+                if (table2.p) {   // release the old table right away (deferred while the scouts run)
+                    if (scouts.active) deferred.push_back(table2.p); else cudaFree(table2.p);
+                    table2 = DevBuf();
+                }
                 n_slots = new_slots;
             }
+        }
+        unsigned long long sc_ctl[SCOUT_CTL_WORDS] = {0};
+        if (n_scouts) {
+            // the search gave up (UNKNOWN) while scouts are still walking: give them a grace period
+            if (hc.stop == 2 && hc.n_undecided > 0) {
+                double grace_s = getenv("JTB_SCOUT_GRACE_MS") ? atof(getenv("JTB_SCOUT_GRACE_MS")) * 1e-3 : 10.0;
+                if (ctx->opts.time_budget_ms)
+                    grace_s = std::max(0.0, ctx->opts.time_budget_ms * 1e-3 - (now_s() - t_start));
+                const double deadline = now_s() + grace_s;
+                while (now_s() < deadline && cudaStreamQuery(ctx->scout_stream) == cudaErrorNotReady)
+                    std::this_thread::sleep_for(std::chrono::microseconds(200));
+            }
+            (void)cudaGetLastError();
+            if (scouts.stop()) { free_tmp(); return -1; }
+            CK(cudaMemcpyAsync(sc_ctl, ctx->sc_ctl.p, sizeof sc_ctl, cudaMemcpyDeviceToHost, ctx->stream));
         }
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         CK(cudaMemcpyAsync(h_found.data(), ctx->found.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -361,7 +521,8 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             st[11] = (unsigned long long)(ms * 1e3);
             st[12] += init_entries.size() * 8 + sizeof(Ctrl) + (size_t)n_shards * 4;
             st[13] = (unsigned long long)attempts * sizeof(Ctrl) + (size_t)n_shards * 8;  // device -> host bytes
-            st[14] = (unsigned long long)(attempts + 2 * (attempts - 1));  // search launches + compact/rehash launches
+            st[14] = (unsigned long long)((scout_only ? 0 : attempts) + 3 * (attempts - 1) + (n_scouts ? 1 : 0));  // search + compact/rehash/re-arm + scouts
+            st[15] = sc_ctl[2]; st[16] = sc_ctl[3]; st[17] = sc_ctl[4]; st[18] = (unsigned long long)n_scouts;
         }
         if (hc.stop == 2 && hc.cause == CAUSE_RING_FULL) hc.cause = JTB_CAUSE_BUDGET;
         for (int s : searchable) {
@@ -428,7 +589,7 @@ double jtb_prepare_info(const jtb_history* h, const jtb_model* m, long long info
 
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n) {
     if (!ctx) return -1;
-    for (int i = 0; i < n && i < 16; ++i) out[i] = ctx->stats[i];
+    for (int i = 0; i < n && i < 20; ++i) out[i] = ctx->stats[i];
     return 0;
 }
 

@@ -373,7 +373,7 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
     out.rank_base.assign(n_shards + 1, 0);
     for (int s = 0; s < n_shards; ++s) out.rank_base[s + 1] = out.rank_base[s] + (int64_t)tmp[s].rets.size();
     out.n_ranks = out.rank_base[n_shards];
-    if (out.n_ranks >= (1ll << 31) - 64) { out.error = "history too large"; return false; }
+    if (out.n_ranks >= (1ll << 29) - 64) { out.error = "history too large"; return false; }  // rank field: 29 bits
     out.rows.assign((size_t)out.n_ranks * RW, 0);
     out.ret_index.assign((size_t)out.n_ranks, -1);
     for (int s = 0; s < n_shards; ++s) {
@@ -384,15 +384,19 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
         const int32_t op_base = (int32_t)out.ops.size();
         // op records (completed ops only live in the table; crashed ones live in class records)
         std::vector<int32_t> gid(t.ops.size(), -1);
+        std::vector<int32_t> op_inv_pos;   // by gid - op_base
         for (int i = 0; i < (int)t.ops.size(); ++i) {
             if (t.ops[i].crashed) continue;
             gid[i] = (int32_t)out.ops.size();
             out.ops.push_back(resolve(h, m, t.ops[i].ret_ev, out));
-            // reads carry their invocation position: the eager-read rule picks the EARLIEST-invoked
-            // consistent read, a choice that does not depend on slot numbering (oracle: first in list order)
-            if ((out.ops.back().x & 0xff) == JTB_F_READ) out.ops.back().w = t.ops[i].inv_pos;
+            // ops carry their invocation position: the eager-read rule picks the EARLIEST-invoked consistent
+            // read (a choice that does not depend on slot numbering; oracle: first in list order) and the
+            // depth-first scouts order their candidates by it.  Bank transfers need .w for the credit slot:
+            // theirs goes into the first (otherwise unused) payload word of the row cell.
+            op_inv_pos.push_back(t.ops[i].inv_pos);
+            const bool transfer = m->kind == JTB_MODEL_BANK && (out.ops.back().x & 0xff) == JTB_F_TRANSFER;
+            if (!transfer) out.ops.back().w = t.ops[i].inv_pos;
         }
-        (void)op_base;
         // class records
         const int32_t cls_base = (int32_t)out.classes.size();
         for (size_t c = 0; c < t.cls_members.size(); ++c) {
@@ -429,8 +433,12 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
                 if (cur[sl] < 0) { cell[0] = OP_EMPTY; continue; }
                 const OpRec& rec = out.ops[cur[sl]];
                 cell[0] = rec.x; cell[1] = rec.y; cell[2] = rec.z; cell[3] = rec.w;
-                if (m->kind == JTB_MODEL_BANK && (rec.x & 0xff) == JTB_F_READ)
-                    std::memcpy(cell + 4, &out.read_bal[(size_t)rec.z * JTB_MAX_ACCOUNTS], 8 * sizeof(int32_t));
+                if (m->kind == JTB_MODEL_BANK) {
+                    if ((rec.x & 0xff) == JTB_F_READ)
+                        std::memcpy(cell + 4, &out.read_bal[(size_t)rec.z * JTB_MAX_ACCOUNTS], 8 * sizeof(int32_t));
+                    else
+                        cell[4] = op_inv_pos[cur[sl] - op_base];
+                }
             }
             out.ret_index[base + j] = h->index[ro.ret_ev];
             cur[ro.slot] = -1;  // the op has returned

@@ -16,11 +16,11 @@ namespace jtb {
 
 // One op as the device sees it (16 B, loaded as int4).
 //   x = f | flags<<8   (flag bit 8: impossible — can never be linearized)
-//   register/cas: y = value / cas-old, z = cas-new
-//   bank transfer: y = amount, z = debit slot, w = credit slot
-//   bank read:     y = care mask over account slots (the balances follow inline in the frontier row)
-//   set add:       y = element value
-//   set read:      (need, care) masks follow inline in the frontier row, per rank
+//   register/cas: y = value / cas-old, z = cas-new, w = invocation position
+//   bank transfer: y = amount, z = debit slot, w = credit slot (invocation position: row cell word 4)
+//   bank read:     y = care mask over account slots (the balances follow inline in the frontier row), w = inv. pos.
+//   set add:       y = element value, w = invocation position
+//   set read:      (need, care) masks follow inline in the frontier row, per rank; w = invocation position
 struct OpRec {
     int32_t x, y, z, w;
 };
@@ -48,7 +48,8 @@ struct ClassRec {
 //   [14..15]   pad
 //   [16 + t*SW, 16 + (t+1)*SW)   the op occupying open-op slot t at that return event, INLINE:
 //        words 0..3  OpRec (x = -1: slot empty)
-//        bank  (SW = 12): words 4..11 = the 8 balances a read expects (by account slot; op.y = care mask)
+//        bank  (SW = 12): words 4..11 = the 8 balances a read expects (by account slot; op.y = care mask);
+//                         word 4 of a TRANSFER = its invocation position
 //        set   (SW = 8):  words 4..7  = (need, care) u64 pair of a read AT THIS RANK:
 //                         consistent <=> (key word1 & care) == need
 constexpr int ROW_EXTRA = 16;

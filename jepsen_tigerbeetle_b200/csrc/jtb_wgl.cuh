@@ -77,12 +77,14 @@ struct WglParams {
     uint32_t deque_cap;     // entries in the CTA's shared-memory deque (power of two)
     int cas_first;          // probe with atom.cas first (experiment switch, env JTB_CAS_FIRST)
     int eager_reads;        // linearize a consistent candidate read immediately and exclusively
-    int max_chain;          // depth-first continuations a warp may take per step (experiment switch JTB_CHAIN)
-    int narrow_cas;         // CAS-first when the CTA's batch is narrow (experiment switch JTB_NARROW_CAS)
 };
 
 constexpr uint64_t KEY_VALID = 1ull << 63;
 constexpr uint64_t KEY_LOCK = 1ull << 62;   // only used by KW > 2 slots while their tail is written
+// Queue entries only (never stored in the table): the config could not be inserted because its probe sequence ran
+// off a full table; whoever pops it inserts it first (after the host has grown the table) — no work is lost.
+constexpr uint64_t KEY_RETRY = 1ull << 61;
+constexpr uint32_t RANK_MASK = 0x1fffffffu;  // global return rank: bits 32..60 of word 0
 constexpr int MAX_PROBE = 512;
 
 // ------------------------------------------------------------------------------------------------
@@ -243,7 +245,7 @@ __device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, co
     constexpr int SW = MODEL == JTB_MODEL_BANK ? 12 : MODEL == JTB_MODEL_SET ? 8 : 4;  // = slot_words(MODEL)
     const int cand_rounds = p.S_pad / 32;
     const int cls_rounds = (p.max_nc + 31) / 32;
-    const int gj = (int)((w[0] >> 32) & 0x3fffffffu);
+    const int gj = (int)((w[0] >> 32) & RANK_MASK);
     const int32_t preg = (int32_t)(uint32_t)w[0];
     const int32_t* row = p.rows + (size_t)gj * p.row_words;
     const int32_t extra = __ldg(row + (lane & 15));
@@ -339,10 +341,12 @@ __device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, co
                 my_probes++;
                 my_max_probe = max(my_max_probe, plen);
                 if (res < 0) {
+                    // table exhausted: pause for growth; the child is queued un-inserted (KEY_RETRY)
                     atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
                     atomicCAS(&ctrl->stop, 0, 2);
+                    cw[0] |= KEY_RETRY;
                 }
-                is_new = res > 0;
+                is_new = res != 0;
                 if (is_new && cgj > gj) {
                     // witness bookkeeping: furthest frontier reached in this shard
                     const unsigned long long wc = *(volatile unsigned long long*)&*wit_cache;
@@ -394,8 +398,9 @@ __device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, co
             if (res < 0) {
                 atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
                 atomicCAS(&ctrl->stop, 0, 2);
+                cw[0] |= KEY_RETRY;
             }
-            is_new = res > 0;
+            is_new = res != 0;
         }
         push(is_new != 0, cw, cbal);
     }
@@ -587,27 +592,18 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
             pre_tail = ld_volatile(&ctrl->tail);
         }
 
-        // narrow phase (few entries): the step is on the search's critical path -> one round trip per insert
-        const bool cas_first = p.cas_first != 0 || (p.narrow_cas && n_batch <= 4);
+        const bool cas_first = p.cas_first != 0;
         // ---- self-scheduled expansion: next staged entry, else one poll of my ring ticket ---------------
         bool polled = false;
         unsigned n_done = 0;
-        [[maybe_unused]] int chain = 0;  // consecutive single-child continuations taken without a barrier
-        bool have_chain = false;
         uint64_t w[KW];
         int32_t pbal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (;;) {
             bool have = false;
-            unsigned idx = 0xffffffffu;
-            if (have_chain) {
-                have = true;        // w / pbal already hold my own single child (depth-first continuation)
-                have_chain = false;
-            } else {
-                if (lane == 0) idx = atomicAdd(&sh.batch_next, 1u);
-                idx = __shfl_sync(0xffffffffu, idx, 0);
-            }
-            if (have) {
-            } else if (idx < n_batch) {
+            unsigned idx = 0;
+            if (lane == 0) idx = atomicAdd(&sh.batch_next, 1u);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx < n_batch) {
                 const uint64_t* e = &s_batch[(size_t)idx * EW];
 #pragma unroll
                 for (int i = 0; i < KW; ++i) w[i] = e[i];
@@ -651,7 +647,6 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
             ++n_done;
             // ---------------- expand (warp-synchronous) ---------------------------------------------
             int n_new_total = 0, n_new_local = 0;
-            unsigned last_base = 0xffffffffu;   // deque index of the most recent local push
 
             auto push_children = [&](bool is_new, const uint64_t (&cw)[KW], const int32_t (&cbal)[8]) {
                 const unsigned newm = __ballot_sync(0xffffffffu, is_new);
@@ -672,7 +667,6 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
                 base = __shfl_sync(0xffffffffu, base, 0);
                 to_ring = __shfl_sync(0xffffffffu, to_ring, 0);
                 const unsigned my = __popc(newm & ((1u << lane) - 1));
-                last_base = to_ring ? 0xffffffffu : base;
                 if (!to_ring) {
                     if (is_new) {
                         uint64_t* e = &s_deque[(size_t)((base + my) & cap_mask) * EW];
@@ -708,8 +702,36 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
                 }
                 n_new_total += n;
             };
-            expand_config<MODEL, KW, EAGER>(p, ctrl, neg_ok, w, pbal, lane, cas_first, &sh.wit_cache, my_probes,
-                                            my_max_probe, push_children);
+            bool expand = true;
+            if (w[0] & KEY_RETRY) {
+                // a child that met a full table (rare: only around a table growth).  It was counted as a config
+                // when it was queued; insert it now: already present -> un-count and drop, still full -> re-queue.
+                w[0] &= ~KEY_RETRY;
+                int res = 0;
+                if (lane == 0) {
+                    int plen;
+                    res = table_insert<KW>(p.table, p.slot_mask, w, &plen, cas_first);
+                }
+                res = __shfl_sync(0xffffffffu, res, 0);
+                if (res <= 0) {
+                    expand = false;
+                    if (lane == 0) { if (my_configs) --my_configs; else atomicAdd(&ctrl->configs, ~0ull); }   // -1
+                    if (res < 0) {
+                        if (lane == 0) {
+                            atomicCAS(&ctrl->cause, 0, JTB_CAUSE_TABLE_FULL);
+                            atomicCAS(&ctrl->stop, 0, 2);
+                        }
+                        uint64_t rw[KW];
+#pragma unroll
+                        for (int i = 0; i < KW; ++i) rw[i] = w[i];
+                        rw[0] |= KEY_RETRY;
+                        push_children(lane == 0, rw, pbal);
+                    }
+                }
+            }
+            if (expand)
+                expand_config<MODEL, KW, EAGER>(p, ctrl, neg_ok, w, pbal, lane, cas_first, &sh.wit_cache, my_probes,
+                                                my_max_probe, push_children);
             if (lane == 0) {
                 if (n_new_local) atomicAdd(&sh.n_new, (unsigned)n_new_local);
                 my_expansions++;
@@ -725,36 +747,6 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
                     }
                 }
             }
-#ifdef JTB_ENABLE_CHAIN
-            // ---- depth-first continuation: exactly one new child, pushed locally and still on top of the
-            //      deque -> take it back (speculative read, then CAS on top) and expand it right away.
-            if (n_new_total == 1 && last_base != 0xffffffffu && chain < p.max_chain) {
-                const uint64_t* e = &s_deque[(size_t)(last_base & cap_mask) * EW];
-                uint64_t cw2[KW];
-                int32_t cb2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-                for (int i = 0; i < KW; ++i) cw2[i] = e[i];
-                if constexpr (L::HAS_BAL) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint64_t v = e[KW + i];
-                        cb2[2 * i] = (int32_t)(uint32_t)v;
-                        cb2[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
-                    }
-                }
-                int got = 0;
-                if (lane == 0) got = atomicCAS(&sh.top, last_base + 1, last_base) == last_base + 1;
-                got = __shfl_sync(0xffffffffu, got, 0);
-                if (got) {
-#pragma unroll
-                    for (int i = 0; i < KW; ++i) w[i] = cw2[i];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) pbal[i] = cb2[i];
-                    have_chain = true;
-                    ++chain;
-                }
-            }
-        #endif
         }
         if (lane == 0 && n_done) atomicAdd(&sh.n_exp, n_done);
     }

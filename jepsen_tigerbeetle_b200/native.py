@@ -82,9 +82,10 @@ class Context:
     """One checker context = one CUDA device + stream + cached device buffers (`jtb_ctx`)."""
 
     def __init__(self, device: int = 0, table_bytes: int = 0, max_configs: int = 0,
-                 time_budget_ms: int = 0, search_ctas: int = 0, eager_reads: bool = True) -> None:
+                 time_budget_ms: int = 0, search_ctas: int = 0, eager_reads: bool = True,
+                 scouts: bool = True) -> None:
         L = lib()
-        flags = 0 if eager_reads else abi.OPT_NO_EAGER_READS
+        flags = (0 if eager_reads else abi.OPT_NO_EAGER_READS) | (0 if scouts else abi.OPT_NO_SCOUTS)
         opts = abi.COpts(device, flags, table_bytes, max_configs, time_budget_ms, search_ctas)
         self._h = L.jtb_create(C.byref(opts))
         if not self._h:
@@ -156,11 +157,12 @@ class Context:
         }
 
     def stats(self) -> dict:
-        out = (C.c_ulonglong * 16)()
-        lib().jtb_get_stats(C.c_void_p(self._h), out, 16)
+        out = (C.c_ulonglong * 20)()
+        lib().jtb_get_stats(C.c_void_p(self._h), out, 20)
         names = ["configs", "probes", "expansions", "ring_tail", "ring_head", "idle_polls",
                  "max_probe_len", "table_slots", "grid", "ring_entries", "attempts", "kernel_us",
-                 "h2d_bytes", "d2h_bytes", "kernel_launches"]
+                 "h2d_bytes", "d2h_bytes", "kernel_launches", "scout_steps", "scout_configs",
+                 "scout_decided", "scouts"]
         return {n: int(out[i]) for i, n in enumerate(names)}
 
     # ---- K2 microbenchmark ----------------------------------------------------------------------

@@ -22,7 +22,5 @@ for rep in range(2):
         env = dict(os.environ)
         if path:
             env["JTB_LIB_PATH"] = path
-        if name == "chain":
-            env["JTB_CHAIN"] = "16"
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
         print(f"rep{rep} {name:10s}: {r.stdout.strip()} {r.stderr.strip()[-200:]}", flush=True)

@@ -15,4 +15,6 @@ with native.Context(max_configs=400_000_000) as ctx:
         m = H.make_model(M[sp.model])
         t = time.perf_counter(); o = oracle.check_linearizable(h, m, 3, eager_reads=True, n_threads=8, max_configs=5_000_000); tc = time.perf_counter() - t
         g = ctx.check_linearizable(h, m)
+        st = ctx.stats()
+        print("   scouts", st["scouts"], "steps", st["scout_steps"], "configs", st["scout_configs"], "decided", st["scout_decided"], flush=True)
         print(sp.model, sp.n_ops, sp.n_clients, sp.p_info, "keys", sp.n_keys, "| gpu", g["valid"], g["configs"], round(g["seconds_total"] * 1e3, 1), "ms | cpu", o["valid"], o["configs"], round(tc * 1e3, 1), "ms", flush=True)

@@ -334,3 +334,75 @@ def test_pause_resume_on_ring_and_table_growth(oracle_mod, monkeypatch):
         assert st["attempts"] >= 2, st
         if not eager:  # the wide exact-space search overruns the tiny ring guard as well
             assert st["attempts"] >= 4 and st["ring_entries"] > (1 << 22), st
+
+
+SCOUT_CASES = [("register", dict(n_ops=400, n_clients=6, p_info=0.1, n_values=5)),
+               ("cas-register", dict(n_ops=600, n_clients=8, p_info=0.2, n_values=5, tau_think_ns=2e6)),
+               ("cas-register", dict(n_ops=2500, n_clients=24, p_info=0.3, n_values=30, tau_think_ns=20e6)),
+               ("bank", dict(n_ops=300, n_clients=6, p_info=0.1, tau_think_ns=4e6)),
+               ("set", dict(n_ops=300, n_clients=5, p_info=0.1)),
+               ("register", dict(n_ops=3000, n_clients=4, p_info=0.0, n_keys=8))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,kw", SCOUT_CASES, ids=[f"{m}-{k['n_ops']}" for m, k in SCOUT_CASES])
+def test_scout_walks_the_cpu_depth_first_order(oracle_mod, monkeypatch, model, kw):
+    """A depth-first scout in order 0 is knossos.wgl's walk: run ALONE (no search kernel) on a valid history it must
+    find the linearization after inserting exactly the configs the CPU port inserts (the port also counts the final,
+    complete config, one per shard; the scout reports success before inserting it)."""
+    from jepsen_tigerbeetle_b200 import native
+    h = synth.generate(synth.SynthSpec(model, seed=11, **kw))
+    m = model_for(model)
+    monkeypatch.setenv("JTB_SCOUT_ONLY", "1")
+    monkeypatch.setenv("JTB_SCOUTS", "1")
+    monkeypatch.setenv("JTB_SCOUT_ORDERS", "1")
+    for eager in (True, False):
+        o = oracle_mod.check_linearizable(h, m, 3, eager_reads=eager)
+        assert o["valid"] == H.VALID
+        with native.Context(eager_reads=eager) as ctx:
+            g = ctx.check_linearizable(h, m)
+            st = ctx.stats()
+        assert g["valid"] == H.VALID, (g, st)
+        assert st["scouts"] == 1 and st["scout_decided"] == h.n_shards, st
+        assert st["scout_configs"] == o["configs"] - h.n_shards, (st, o["configs"])
+
+
+@pytest.mark.gpu
+def test_scouts_rescue_crash_heavy_valid_histories(oracle_mod):
+    """Found by the soak test: valid histories with 10-30 % crashed ops, where breadth-first exploration runs out of
+    budget (:unknown) but a depth-first walk finds the linearization.  With scouts the verdict is VALID; without,
+    the same budget gives UNKNOWN (never a wrong answer)."""
+    from jepsen_tigerbeetle_b200 import native
+    specs = [synth.SynthSpec('cas-register', 2500, 24, 809007372, p_info=0.3, tau_think_ns=20e6, n_values=30),
+             synth.SynthSpec('register', 1000, 24, 902980068, p_info=0.3, tau_think_ns=5e6, n_values=30, stale_read=True)]
+    for sp in specs:
+        h = synth.generate(sp)
+        m = model_for(sp.model)
+        assert oracle_mod.check_linearizable(h, m, 3, eager_reads=True, max_configs=5_000_000)["valid"] == H.VALID
+        with native.Context(max_configs=50_000_000) as ctx:
+            g = ctx.check_linearizable(h, m)
+            st = ctx.stats()
+        assert g["valid"] == H.VALID, (g, st)
+        assert st["scouts"] == 4, st
+        with native.Context(max_configs=50_000_000, scouts=False) as ctx:
+            g0 = ctx.check_linearizable(h, m)
+            assert ctx.stats()["scouts"] == 0
+        assert g0["valid"] in (H.VALID, H.UNKNOWN)
+
+
+@pytest.mark.gpu
+def test_scouts_do_not_disturb_exhaustive_counts_or_growth(oracle_mod, monkeypatch):
+    """An INVALID history with crashed ops: scouts run beside the search (they can never decide it), the table is
+    re-hashed several times while they run (deferred frees), and the exhaustive count still equals the oracle's."""
+    from jepsen_tigerbeetle_b200 import native
+    h = synth.generate(synth.SynthSpec("bank", 3000, 16, 1, p_info=0.02, stale_read=True, tau_think_ns=4e6))
+    m = model_for("bank")
+    o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True, max_configs=50_000_000)
+    assert o["valid"] == H.INVALID
+    monkeypatch.setenv("JTB_TABLE_START_MB", "1")
+    with native.Context() as ctx:
+        g = ctx.check_linearizable(h, m)
+        st = ctx.stats()
+    same_verdict(g, o)
+    assert g["configs"] == o["configs"], (st, o["configs"])
+    assert st["scouts"] == 4 and st["scout_decided"] == 0, st
