@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(32) wgl_scout_kernel(const WglParams p, const 
         uint32_t cursor = 0;   // smallest priority not yet tried at the current config
         int top = 0;           // the current config is stack[top]
         unsigned long long steps = 0;
+        unsigned visits = 0;
         // the shard's class records: one dependent global round trip less per step when they sit in shared memory
         const int4* cls_tab;
         {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(32) wgl_scout_kernel(const WglParams p, const 
         }
 
         for (;;) {
-            if ((steps & 15) == 0) {
+            if ((visits++ & 15) == 0) {
                 int s = 0;
                 if (lane == 0) s = ld_volatile(&sp.ctl[1]) != 0 || ld_volatile(&ctrl->n_undecided) <= 0;
                 if (__shfl_sync(FULL, s, 0)) { quit = true; break; }
@@ -132,27 +133,34 @@ __global__ void __launch_bounds__(32) wgl_scout_kernel(const WglParams p, const 
                 if (lane == 0) f = ld_volatile(&p.shard_found[shard]);
                 if (__shfl_sync(FULL, f, 0)) break;   // somebody decided this shard
             }
-            // ---- pick the next child: smallest priority >= cursor among the consistent candidates -------
-            uint32_t best = NONE, ebest = NONE;
-            int best_id = -1, ebest_id = -1;
-            for (int r = 0; r < cand_rounds; ++r) {
-                const int t = r * 32 + lane;
-                const int32_t* cell = row + ROW_EXTRA + t * SW;
-                const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
-                const bool cand = op.x >= 0 && !((w[1] >> t) & 1ull);
-                int32_t creg = preg;
-                int32_t cbal[8];
+            // ---- evaluate every candidate ONCE per visit; lane-private priorities (NONE = not a consistent child) ----
+            constexpr int SR = 2, CR = 4;     // cached rounds: 64 slots, 128 classes (more classes: re-evaluate)
+            uint32_t prs[SR], prc[CR];
+            uint32_t xbest = NONE, ebest = NONE;   // xbest: best of the un-cached class rounds (filtered by cursor)
+            int xbest_id = -1, ebest_id = -1;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-                const bool ok = cand && model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
-                if (ok) {
-                    const bool is_read = (op.x & 0xff) == JTB_F_READ;
-                    const uint32_t ipos = (uint32_t)((BANK && !is_read) ? __ldg(cell + 4) : op.w);
-                    if (EAGER && is_read && ipos < ebest) { ebest = ipos; ebest_id = t; }
-                    const uint32_t pr = scout_prio(order, ipos, t == rslot, false);
-                    if (pr >= cursor && pr < best) { best = pr; best_id = t; }
+            for (int r = 0; r < SR; ++r) {
+                prs[r] = NONE;
+                if (r < cand_rounds) {
+                    const int t = r * 32 + lane;
+                    const int32_t* cell = row + ROW_EXTRA + t * SW;
+                    const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
+                    const bool cand = op.x >= 0 && !((w[1] >> t) & 1ull);
+                    int32_t creg = preg;
+                    int32_t cbal[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+                    const bool ok = cand && model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
+                    if (ok) {
+                        const bool is_read = (op.x & 0xff) == JTB_F_READ;
+                        const uint32_t ipos = (uint32_t)((BANK && !is_read) ? __ldg(cell + 4) : op.w);
+                        if (EAGER && is_read && ipos < ebest) { ebest = ipos; ebest_id = t; }
+                        prs[r] = scout_prio(order, ipos, t == rslot, false);
+                    }
                 }
             }
+#pragma unroll
+            for (int r = 0; r < CR; ++r) prc[r] = NONE;
             for (int r = 0; r < cls_rounds; ++r) {
                 const int c = r * 32 + lane;
                 bool cand = c < ncls;
@@ -179,137 +187,159 @@ __global__ void __launch_bounds__(32) wgl_scout_kernel(const WglParams p, const 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
                 const bool ok = cand && model_step<MODEL>(cop, creg, cbal, nullptr, neg_ok != 0, w[1]);
-                if (ok) {
-                    const uint32_t pr = scout_prio(order, ipos, false, true);
-                    if (pr >= cursor && pr < best) { best = pr; best_id = CLASS_ID + c; }
-                }
+                const uint32_t pr = ok ? scout_prio(order, ipos, false, true) : NONE;
+                if (r < CR) {
+#pragma unroll
+                    for (int k = 0; k < CR; ++k) if (k == r) prc[k] = pr;
+                } else if (pr >= cursor && pr < xbest) { xbest = pr; xbest_id = CLASS_ID + c; }
             }
-            int pick = -1;
-            uint32_t next_cursor = NONE;
+            const bool cached = cls_rounds <= CR;   // all priorities are in registers: siblings need no re-evaluation
             const uint32_t emn = EAGER ? __reduce_min_sync(FULL, ebest) : NONE;
-            if (emn != NONE) {
-                // eager reads: the earliest-invoked consistent read is the ONLY child of this config
-                if (cursor == 0) {
-                    const unsigned who = __ballot_sync(FULL, ebest == emn);
-                    pick = __shfl_sync(FULL, ebest_id, __ffs(who) - 1);
-                }
-            } else {
-                const uint32_t mn = __reduce_min_sync(FULL, best);
-                if (mn != NONE) {
-                    const unsigned who = __ballot_sync(FULL, best == mn);
-                    pick = __shfl_sync(FULL, best_id, __ffs(who) - 1);
-                    next_cursor = mn + 1;
-                }
-            }
-            if (pick < 0) {
-                // ---- every child tried: backtrack ------------------------------------------------------
-                if (top == 0) break;   // this order is exhausted without a linearization: no verdict
-                --top;
-                __syncwarp();
-                const uint64_t* fr = stack + (size_t)top * FW;
-#pragma unroll
-                for (int i = 0; i < KW; ++i) w[i] = __ldcg(fr + i);
-                if constexpr (BANK) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint64_t v = __ldcg(fr + KW + i);
-                        pbal[2 * i] = (int32_t)(uint32_t)v;
-                        pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+            bool leave_pair = false;
+            // ---- siblings in priority order: the first child that is new becomes the current config ---------------
+            for (;;) {
+                int pick = -1;
+                uint32_t next_cursor = NONE;
+                if (emn != NONE) {
+                    // eager reads: the earliest-invoked consistent read is the ONLY child of this config
+                    if (cursor == 0) {
+                        const unsigned who = __ballot_sync(FULL, ebest == emn);
+                        pick = __shfl_sync(FULL, ebest_id, __ffs(who) - 1);
                     }
-                }
-                cursor = (uint32_t)__ldcg(fr + EW);
-                continue;
-            }
-            // ---- build the child (all lanes compute the same values) --------------------------------------
-            uint64_t cw[KW];
-#pragma unroll
-            for (int i = 0; i < KW; ++i) cw[i] = w[i];
-            int32_t creg = preg;
-            int32_t cbal[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
-            int cgj = gj;
-            if (pick < CLASS_ID) {
-                const int t = pick;
-                const int32_t* cell = row + ROW_EXTRA + t * SW;
-                const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
-                model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
-                if (t == rslot) {
-                    // the frontier op is linearized: the frontier passes every already-linearized return
-                    uint64_t m = w[1];
-                    int adv = 0;
-                    const int32_t* rw = row;
-                    int32_t ex = extra;
-                    for (;;) {
-                        const int32_t word = __shfl_sync(FULL, ex, lane >> 2);
-                        const int sl = (word >> (8 * (lane & 3))) & 0xff;
-                        const bool setb = sl != 0xff && ((m >> sl) & 1ull);
-                        const unsigned peers = __match_any_sync(FULL, sl);
-                        const bool pass = setb && (peers & ((1u << lane) - 1)) == 0;
-                        const unsigned pm = __ballot_sync(FULL, pass);
-                        const int n = pm == FULL ? 32 : __ffs(~pm) - 1;
-                        const uint64_t clr = (lane < n) ? (1ull << sl) : 0ull;
-                        const uint32_t clo = __reduce_or_sync(FULL, (uint32_t)clr);
-                        const uint32_t chi = __reduce_or_sync(FULL, (uint32_t)(clr >> 32));
-                        m &= ~((uint64_t)clo | ((uint64_t)chi << 32));
-                        adv += n;
-                        if (n < 32) break;
-                        rw += (size_t)32 * p.row_words;
-                        ex = __ldg(rw + (lane & 15));
-                    }
-                    cgj = gj + 1 + adv;
-                    cw[1] = m;
                 } else {
-                    cw[1] |= 1ull << t;
-                }
-            } else {
-                const int4 b = cls_tab[2 * (pick - CLASS_ID) + 1];
-                const int4 cop = cls_tab[2 * (pick - CLASS_ID)];
-                model_step<MODEL>(cop, creg, cbal, nullptr, neg_ok != 0, w[1]);
-                const int shift = b.w & 0xff;
+                    uint32_t best = xbest;
+                    int best_id = xbest_id;
 #pragma unroll
-                for (int i = 1; i < KW; ++i) if (i == b.z) cw[i] += 1ull << shift;
-            }
-            cw[0] = KEY_VALID | ((uint64_t)(uint32_t)cgj << 32) |
-                    ((BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
-            cursor = next_cursor;
-            if (cgj >= gj_end) {
-                // every :ok op of the shard is linearized -> VALID (same bookkeeping as the crowd)
-                if (lane == 0 && atomicExch(&p.shard_found[shard], 1) == 0) {
-                    ++decided;
-                    const int left = atomicSub(&ctrl->n_undecided, 1);
-                    __threadfence();
-                    if (left == 1) atomicCAS(&ctrl->stop, 0, 1);
+                    for (int r = 0; r < SR; ++r)
+                        if (prs[r] != NONE && prs[r] >= cursor && prs[r] < best) { best = prs[r]; best_id = r * 32 + lane; }
+#pragma unroll
+                    for (int r = 0; r < CR; ++r)
+                        if (prc[r] != NONE && prc[r] >= cursor && prc[r] < best) { best = prc[r]; best_id = CLASS_ID + r * 32 + lane; }
+                    const uint32_t mn = __reduce_min_sync(FULL, best);
+                    if (mn != NONE) {
+                        const unsigned who = __ballot_sync(FULL, best == mn);
+                        pick = __shfl_sync(FULL, best_id, __ffs(who) - 1);
+                        next_cursor = mn + 1;
+                    }
                 }
+                if (pick < 0) {
+                    // ---- every child tried: backtrack ---------------------------------------------------
+                    if (top == 0) { leave_pair = true; break; }   // order exhausted without a linearization: no verdict
+                    --top;
+                    __syncwarp();
+                    const uint64_t* fr = stack + (size_t)top * FW;
+#pragma unroll
+                    for (int i = 0; i < KW; ++i) w[i] = __ldcg(fr + i);
+                    if constexpr (BANK) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t v = __ldcg(fr + KW + i);
+                            pbal[2 * i] = (int32_t)(uint32_t)v;
+                            pbal[2 * i + 1] = (int32_t)(uint32_t)(v >> 32);
+                        }
+                    }
+                    cursor = (uint32_t)__ldcg(fr + EW);
+                    break;
+                }
+                // ---- build the child (all lanes compute the same values) ----------------------------------
+                uint64_t cw[KW];
+#pragma unroll
+                for (int i = 0; i < KW; ++i) cw[i] = w[i];
+                int32_t creg = preg;
+                int32_t cbal[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cbal[i] = pbal[i];
+                int cgj = gj;
+                if (pick < CLASS_ID) {
+                    const int t = pick;
+                    const int32_t* cell = row + ROW_EXTRA + t * SW;
+                    const int4 op = __ldg(reinterpret_cast<const int4*>(cell));
+                    model_step<MODEL>(op, creg, cbal, cell, neg_ok != 0, w[1]);
+                    if (t == rslot) {
+                        // the frontier op is linearized: the frontier passes every already-linearized return
+                        uint64_t m = w[1];
+                        int adv = 0;
+                        const int32_t* rw = row;
+                        int32_t ex = extra;
+                        for (;;) {
+                            const int32_t word = __shfl_sync(FULL, ex, lane >> 2);
+                            const int sl = (word >> (8 * (lane & 3))) & 0xff;
+                            const bool setb = sl != 0xff && ((m >> sl) & 1ull);
+                            const unsigned peers = __match_any_sync(FULL, sl);
+                            const bool pass = setb && (peers & ((1u << lane) - 1)) == 0;
+                            const unsigned pm = __ballot_sync(FULL, pass);
+                            const int n = pm == FULL ? 32 : __ffs(~pm) - 1;
+                            const uint64_t clr = (lane < n) ? (1ull << sl) : 0ull;
+                            const uint32_t clo = __reduce_or_sync(FULL, (uint32_t)clr);
+                            const uint32_t chi = __reduce_or_sync(FULL, (uint32_t)(clr >> 32));
+                            m &= ~((uint64_t)clo | ((uint64_t)chi << 32));
+                            adv += n;
+                            if (n < 32) break;
+                            rw += (size_t)32 * p.row_words;
+                            ex = __ldg(rw + (lane & 15));
+                        }
+                        cgj = gj + 1 + adv;
+                        cw[1] = m;
+                    } else {
+                        cw[1] |= 1ull << t;
+                    }
+                } else {
+                    const int4 b = cls_tab[2 * (pick - CLASS_ID) + 1];
+                    const int4 cop = cls_tab[2 * (pick - CLASS_ID)];
+                    model_step<MODEL>(cop, creg, cbal, nullptr, neg_ok != 0, w[1]);
+                    const int shift = b.w & 0xff;
+#pragma unroll
+                    for (int i = 1; i < KW; ++i) if (i == b.z) cw[i] += 1ull << shift;
+                }
+                cw[0] = KEY_VALID | ((uint64_t)(uint32_t)cgj << 32) |
+                        ((BANK || MODEL == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)creg);
+                cursor = next_cursor;
+                if (cgj >= gj_end) {
+                    // every :ok op of the shard is linearized -> VALID (same bookkeeping as the crowd)
+                    if (lane == 0 && atomicExch(&p.shard_found[shard], 1) == 0) {
+                        ++decided;
+                        const int left = atomicSub(&ctrl->n_undecided, 1);
+                        __threadfence();
+                        if (left == 1) atomicCAS(&ctrl->stop, 0, 1);
+                    }
+                    leave_pair = true;
+                    break;
+                }
+                int res = 0;
+                if (lane == 0) {
+                    int plen;
+                    res = table_insert<KW>(table, sp.slot_mask, cw, &plen, /*cas_first=*/true);   // private table: one round trip
+                }
+                res = __shfl_sync(FULL, res, 0);
+                if (res < 0) { quit = true; leave_pair = true; break; }
+                if (res == 0) {
+                    // seen before: next sibling (straight from the cached priorities when they are complete)
+                    if (!cached) break;
+                    ++steps;
+                    continue;
+                }
+                ++inserts;
+                if ((uint32_t)(top + 1) >= sp.stack_cap) { leave_pair = true; break; }   // cannot happen: depth <= ops
+                if (lane == 0) {
+                    __stcg(stack + (size_t)top * FW + EW, (uint64_t)cursor);   // where the parent resumes
+                    uint64_t* fr = stack + (size_t)(top + 1) * FW;
+#pragma unroll
+                    for (int i = 0; i < KW; ++i) __stcg(fr + i, cw[i]);
+                    if constexpr (BANK) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            __stcg(fr + KW + i, (uint64_t)(uint32_t)cbal[2 * i] | ((uint64_t)(uint32_t)cbal[2 * i + 1] << 32));
+                    }
+                }
+                ++top;
+#pragma unroll
+                for (int i = 0; i < KW; ++i) w[i] = cw[i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pbal[i] = cbal[i];
+                cursor = 0;
                 break;
             }
-            int res = 0;
-            if (lane == 0) {
-                int plen;
-                res = table_insert<KW>(table, sp.slot_mask, cw, &plen, /*cas_first=*/true);   // private table: one round trip
-            }
-            res = __shfl_sync(FULL, res, 0);
-            if (res < 0) { quit = true; break; }
-            if (res == 0) continue;   // seen before: next sibling
-            ++inserts;
-            if ((uint32_t)(top + 1) >= sp.stack_cap) break;   // deeper than the shard has ops: cannot happen
-            if (lane == 0) {
-                __stcg(stack + (size_t)top * FW + EW, (uint64_t)cursor);   // where the parent resumes
-                uint64_t* fr = stack + (size_t)(top + 1) * FW;
-#pragma unroll
-                for (int i = 0; i < KW; ++i) __stcg(fr + i, cw[i]);
-                if constexpr (BANK) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        __stcg(fr + KW + i, (uint64_t)(uint32_t)cbal[2 * i] | ((uint64_t)(uint32_t)cbal[2 * i + 1] << 32));
-                }
-            }
-            ++top;
-#pragma unroll
-            for (int i = 0; i < KW; ++i) w[i] = cw[i];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pbal[i] = cbal[i];
-            cursor = 0;
+            if (leave_pair) break;
         }
         steps_total += steps;
     }
