@@ -491,7 +491,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         if (n_scouts) {
             // the search gave up (UNKNOWN) while scouts are still walking: give them a grace period
             if (hc.stop == 2 && hc.n_undecided > 0) {
-                double grace_s = getenv("JTB_SCOUT_GRACE_MS") ? atof(getenv("JTB_SCOUT_GRACE_MS")) * 1e-3 : 10.0;
+                double grace_s = getenv("JTB_SCOUT_GRACE_MS") ? atof(getenv("JTB_SCOUT_GRACE_MS")) * 1e-3 : 20.0;
                 if (ctx->opts.time_budget_ms)
                     grace_s = std::max(0.0, ctx->opts.time_budget_ms * 1e-3 - (now_s() - t_start));
                 const double deadline = now_s() + grace_s;

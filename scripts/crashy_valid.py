@@ -8,6 +8,7 @@ specs = [synth.SynthSpec('cas-register', 2500, 24, 809007372, p_info=0.3, tau_th
          synth.SynthSpec('register', 2500, 40, 321354213, p_info=0.1, tau_think_ns=20e6, n_values=30, stale_by=3),
          synth.SynthSpec('cas-register', 1000, 16, 1, p_info=0.05), synth.SynthSpec('cas-register', 50000, 2048, 1, p_info=0.3, n_keys=256, grouped_keys=True),
          synth.SynthSpec('cas-register', 50000, 64, 1, p_info=0.3, n_keys=8, grouped_keys=True)]
+rows = []
 M = {"register": H.MODEL_REGISTER, "cas-register": H.MODEL_CAS_REGISTER}
 with native.Context(max_configs=400_000_000) as ctx:
     for sp in specs:
@@ -17,4 +18,10 @@ with native.Context(max_configs=400_000_000) as ctx:
         g = ctx.check_linearizable(h, m)
         st = ctx.stats()
         print("   scouts", st["scouts"], "steps", st["scout_steps"], "configs", st["scout_configs"], "decided", st["scout_decided"], flush=True)
+        rows.append({"model": sp.model, "n_ops": sp.n_ops, "n_clients": sp.n_clients, "p_info": sp.p_info, "n_keys": sp.n_keys,
+                     "gpu_valid": g["valid"], "gpu_configs": g["configs"], "gpu_seconds": g["seconds_total"],
+                     "scout_steps": st["scout_steps"], "scout_configs": st["scout_configs"], "scout_decided": st["scout_decided"],
+                     "cpu_valid": o["valid"], "cpu_configs": o["configs"], "cpu_seconds": tc})
         print(sp.model, sp.n_ops, sp.n_clients, sp.p_info, "keys", sp.n_keys, "| gpu", g["valid"], g["configs"], round(g["seconds_total"] * 1e3, 1), "ms | cpu", o["valid"], o["configs"], round(tc * 1e3, 1), "ms", flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(rows, open("gpurun_out/crashy_valid.json", "w"), indent=1)
