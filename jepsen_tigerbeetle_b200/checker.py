@@ -18,7 +18,7 @@ Histories may be given as Jepsen op maps (list of dicts) or as an already flatte
 from __future__ import annotations
 
 import traceback
-from typing import Any, Callable, Mapping, Sequence
+from typing import Any, Mapping
 
 import numpy as np
 

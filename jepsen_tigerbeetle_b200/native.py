@@ -10,10 +10,8 @@ import os
 import subprocess
 import threading
 
-import numpy as np
-
 from . import abi
-from .history import CHistory, CModel, FlatHistory, as_c_history
+from .history import CModel, FlatHistory, as_c_history
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JTB_LIB_PATH") or os.path.join(_HERE, "libjtb_check.so")  # env: A/B experiments only

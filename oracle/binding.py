@@ -5,8 +5,6 @@ import ctypes as C
 import os
 import subprocess
 
-import numpy as np
-
 from jepsen_tigerbeetle_b200 import abi
 from jepsen_tigerbeetle_b200.history import CModel, FlatHistory, as_c_history
 
