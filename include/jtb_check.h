@@ -221,7 +221,7 @@ typedef struct jtb_ctx jtb_ctx;
 int         jtb_abi_version(void);
 /* sizeof of the ABI structs as this library was compiled, for binding self-checks:
  * 0 jtb_history, 1 jtb_model, 2 jtb_opts, 3 jtb_lin_shard, 4 jtb_lin_result, 5 jtb_setfull_shard,
- * 6 jtb_setfull_out, 7 jtb_bank_result; -1 otherwise */
+ * 6 jtb_setfull_out, 7 jtb_bank_result, 8 jtb_final_config; -1 otherwise */
 long        jtb_struct_size(int which);
 int         jtb_device_count(void);                 /* number of CUDA devices, <0 on error          */
 jtb_ctx*    jtb_create(const jtb_opts* opts);       /* NULL on failure (no CUDA device etc.)        */
@@ -235,6 +235,27 @@ const char* jtb_last_error(const jtb_ctx* ctx);     /* valid until the next call
  * (jtb_last_error; glue throws so that jepsen's check-safe yields {:valid? :unknown}).          */
 int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m,
                            jtb_lin_shard* shards, jtb_lin_result* out);
+
+/* ---- knossos analysis :configs ------------------------------------------------ *
+ * The configurations alive where an INVALID shard got stuck: every visited configuration whose first
+ * un-linearized :ok return is the witness (`:op`).  knossos reports them as {:model :pending ...} maps and
+ * jepsen.checker/linearizable keeps the first 10.  Call directly after a jtb_check_linearizable(ctx, h, m, ..)
+ * that reported JTB_INVALID for `shard`, with the SAME h and m (the visited table of that search is read;
+ * any other call on ctx invalidates it).  Writes min(cap, *n_total) configurations in a canonical order
+ * (ascending, lexicographic over the struct's int32 fields in declaration order; unused entries are 0).
+ * Returns 0, <0 on error. */
+typedef struct jtb_final_config {
+    int32_t state;                          /* register / cas-register value (JTB_NIL = nil); 0 for bank, set */
+    int32_t balances[JTB_MAX_ACCOUNTS];     /* bank: balance per account slot                                  */
+    int32_t n_pending;                      /* completed ops open at the witness' return, NOT linearized
+                                               (the witness itself is one of them)                             */
+    int32_t n_linearized_open;              /* completed ops open at the witness' return, already linearized   */
+    int32_t n_crashed_linearized;           /* crashed (:info) ops linearized in this configuration            */
+    int32_t pending_index[64];              /* :index of their invocations, ascending                          */
+    int32_t linearized_open_index[64];
+} jtb_final_config;
+int jtb_final_configs(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, int32_t shard,
+                      jtb_final_config* out, int32_t cap, int64_t* n_total);
 
 /* ---- hot path A4: (checker/set-full {:linearizable? L}) at set_full.clj:157 ------------------ */
 int jtb_check_set_full(jtb_ctx* ctx, const jtb_history* h, int linearizable, jtb_setfull_out* out);

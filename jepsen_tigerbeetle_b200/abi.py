@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-from .history import MAX_ACCOUNTS  # noqa: F401  (re-exported for convenience)
+from .history import MAX_ACCOUNTS
 
 ABI_VERSION = 1
 OPT_NO_EAGER_READS = 1
@@ -26,6 +26,20 @@ class CLinShard(C.Structure):
     _fields_ = [("valid", C.c_int32), ("witness_index", C.c_int32),
                 ("previous_ok_index", C.c_int32), ("cause", C.c_int32),
                 ("configs_explored", C.c_uint64), ("probes", C.c_uint64)]
+
+
+class CFinalConfig(C.Structure):
+    """jtb_final_config: one of knossos' :configs of an INVALID shard."""
+    _fields_ = [("state", C.c_int32), ("balances", C.c_int32 * MAX_ACCOUNTS), ("n_pending", C.c_int32),
+                ("n_linearized_open", C.c_int32), ("n_crashed_linearized", C.c_int32),
+                ("pending_index", C.c_int32 * 64), ("linearized_open_index", C.c_int32 * 64)]
+
+
+def final_configs_to_list(buf, n: int) -> list[dict]:
+    return [{"state": c.state, "balances": list(c.balances),
+             "pending": list(c.pending_index[:c.n_pending]),
+             "linearized_open": list(c.linearized_open_index[:c.n_linearized_open]),
+             "crashed_linearized": c.n_crashed_linearized} for c in buf[:n]]
 
 
 class CLinResult(C.Structure):

@@ -81,7 +81,8 @@ class _Native:
 class Linearizable(Checker, _Native):
     """`(checker/linearizable {:model m})` — knossos analysis on the GPU (hot path A9).
 
-    Result keys follow knossos: valid?, op (witness :index), previous-ok, configs-explored, analyzer,
+    Result keys follow knossos: valid?, op (witness :index), previous-ok, configs (the configurations stuck at the
+    witness, first 10 as jepsen.checker/linearizable keeps them, plus configs-total), configs-explored, analyzer,
     cause (when :unknown).  For keyed histories use `independent_checker(linearizable(...))`."""
 
     def __init__(self, model: str, ctx: Context | None = None, init_value=None, **ctx_opts) -> None:
@@ -101,15 +102,32 @@ class Linearizable(Checker, _Native):
         from .history import NIL
         return make_model(kind, init_value=NIL if self.init_value is None else int(self.init_value))
 
+    def _render_config(self, cm, c: dict) -> dict:
+        from .history import NIL
+        kind = _MODEL_KIND[self.model]
+        if kind == MODEL_BANK:
+            model = {int(cm.account_ids[i]): c["balances"][i] for i in range(cm.n_accounts)}
+        elif kind == MODEL_SET:
+            model = None   # the set is the union of the linearized adds
+        else:
+            model = None if c["state"] == NIL else c["state"]
+        return {"model": model, "pending": [{"index": i} for i in c["pending"]],
+                "linearized-open": [{"index": i} for i in c["linearized_open"]],
+                "crashed-linearized": c["crashed_linearized"]}
+
     def check_flat(self, test, h: FlatHistory) -> tuple[dict, list[dict]]:
-        r = self.ctx.check_linearizable(h, self._cmodel(test))
+        cm = self._cmodel(test)
+        r = self.ctx.check_linearizable(h, cm)
         per = []
-        for s in r["shards"]:
+        for k, s in enumerate(r["shards"]):
             m = {"valid?": VERDICT_NAME[s["valid"]], "analyzer": "wgl-gpu"}
             if s["valid"] == INVALID:
                 m["op"] = {"index": s["witness_index"]}
                 m["previous-ok"] = ({"index": s["previous_ok_index"]}
                                     if s["previous_ok_index"] >= 0 else None)
+                fc = self.ctx.final_configs(h, cm, shard=k, cap=10)   # reads the table of the search just done
+                m["configs"] = [self._render_config(cm, c) for c in fc["configs"]]
+                m["configs-total"] = fc["total"]
             if s["valid"] == UNKNOWN:
                 m["cause"] = abi.CAUSE_NAME.get(s["cause"], "unknown")
             per.append(m)

@@ -36,6 +36,14 @@ struct jtb_ctx {
     DevBuf sc_init, sc_tables, sc_stacks, sc_ctl;   // scouts: initial entries, private tables, stacks, control words
     unsigned long long stats[20] = {0};
     unsigned long long last_configs = 0;  // configs of the previous search (sizes the next table)
+    // what jtb_final_configs needs from the last search (its visited table is still in `table`)
+    struct {
+        bool valid = false;
+        int64_t n_events = 0;
+        int n_shards = 0, kw = 0;
+        uint64_t n_slots = 0;
+        std::vector<int> max_rank, verdict;
+    } fc;
 };
 
 namespace {
@@ -183,6 +191,7 @@ long jtb_struct_size(int which) {
     case 5: return sizeof(jtb_setfull_shard);
     case 6: return sizeof(jtb_setfull_out);
     case 7: return sizeof(jtb_bank_result);
+    case 8: return sizeof(jtb_final_config);
     }
     return -1;
 }
@@ -241,6 +250,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     if (!ctx) return -1;
     std::lock_guard<std::mutex> lk(ctx->mu);
     const double t_start = now_s();
+    ctx->fc.valid = false;
     CK(cudaSetDevice(ctx->device));
     if (m->kind != JTB_MODEL_REGISTER && m->kind != JTB_MODEL_CAS_REGISTER && m->kind != JTB_MODEL_BANK &&
         m->kind != JTB_MODEL_SET) {
@@ -543,6 +553,14 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             shards[0].configs_explored = configs;
             shards[0].probes = probes;
         }
+        ctx->fc.valid = !scout_only;
+        ctx->fc.n_events = h->n_events;
+        ctx->fc.n_shards = n_shards;
+        ctx->fc.kw = KW;
+        ctx->fc.n_slots = n_slots;
+        ctx->fc.max_rank = h_max;
+        ctx->fc.verdict.assign(n_shards, JTB_UNKNOWN);
+        for (int s = 0; s < n_shards; ++s) ctx->fc.verdict[s] = shards[s].valid;
     }
     for (int s = 0; s < n_shards; ++s) {
         out->valid = std::max(out->valid, shards[s].valid);
@@ -557,10 +575,130 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
 }
 
 // -------------------------------------------------------------------------------------------------
+// knossos :configs for an INVALID shard: the visited configurations stuck at the witness
+int jtb_final_configs(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, int32_t shard, jtb_final_config* out,
+                      int32_t cap, int64_t* n_total) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->fc.valid || h->n_events != ctx->fc.n_events || h->n_shards != ctx->fc.n_shards || shard < 0 ||
+        shard >= h->n_shards) {
+        ctx->err = "jtb_final_configs: call it directly after jtb_check_linearizable on the same history";
+        return -2;
+    }
+    if (ctx->fc.verdict[shard] != JTB_INVALID) {
+        ctx->err = "jtb_final_configs: the shard was not found INVALID";
+        return -2;
+    }
+    Prepared P;
+    if (!prepare(h, m, P) || P.key_words != ctx->fc.kw) {
+        ctx->err = "jtb_final_configs: the history does not match the last search";
+        return -3;
+    }
+    const int KW = P.key_words, RW = P.row_words, SW = slot_words(m->kind);
+    const bool bank = m->kind == JTB_MODEL_BANK;
+    const int64_t g = ctx->fc.max_rank[shard], base = P.rank_base[shard];
+    // ---- gather the keys at rank g ------------------------------------------------------------------
+    std::vector<uint64_t> keys;
+    if (g == base) {   // the initial configuration is never inserted
+        keys.assign(KW, 0);
+        keys[0] = KEY_VALID | ((uint64_t)(uint32_t)base << 32) |
+                  ((bank || m->kind == JTB_MODEL_SET) ? 0ull : (uint64_t)(uint32_t)m->init_value);
+    }
+    {
+        DevBuf d_cnt, d_out;
+        auto free_all = [&]() { if (d_cnt.p) cudaFree(d_cnt.p); if (d_out.p) cudaFree(d_out.p); };
+        if (ensure(ctx, d_cnt, 8)) return -1;
+        const uint64_t* table = (const uint64_t*)ctx->table.p;
+        unsigned long long total = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            const unsigned long long want = pass == 0 ? 0 : std::min<unsigned long long>(total, 1ull << 22);
+            if (pass == 1 && want == 0) break;
+            if (pass == 1 && ensure(ctx, d_out, want * KW * 8)) { free_all(); return -1; }
+            CK(cudaMemsetAsync(d_cnt.p, 0, 8, ctx->stream));
+            const int grid = ctx->n_sms * 8;
+            if (KW == 2) table_collect_kernel<2><<<grid, 256, 0, ctx->stream>>>(table, ctx->fc.n_slots, (uint32_t)g, (uint64_t*)d_out.p, want, (unsigned long long*)d_cnt.p);
+            else if (KW == 4) table_collect_kernel<4><<<grid, 256, 0, ctx->stream>>>(table, ctx->fc.n_slots, (uint32_t)g, (uint64_t*)d_out.p, want, (unsigned long long*)d_cnt.p);
+            else table_collect_kernel<8><<<grid, 256, 0, ctx->stream>>>(table, ctx->fc.n_slots, (uint32_t)g, (uint64_t*)d_out.p, want, (unsigned long long*)d_cnt.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&total, d_cnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (pass == 1) {
+                const size_t off = keys.size();
+                keys.resize(off + (size_t)want * KW);
+                CK(cudaMemcpy(keys.data() + off, d_out.p, (size_t)want * KW * 8, cudaMemcpyDeviceToHost));
+            }
+        }
+        free_all();
+        *n_total = (int64_t)total + (g == base ? 1 : 0);
+    }
+    // ---- decode -----------------------------------------------------------------------------------------
+    std::vector<int32_t> pos_index;   // client-event position inside the shard -> :index
+    for (int64_t e = h->shard_off[shard]; e < h->shard_off[shard + 1]; ++e)
+        if (h->process[e] >= 0) pos_index.push_back(h->index[e]);
+    const int32_t* row = &P.rows[(size_t)g * RW];
+    const int cls_base = row[11], ncls = row[12];
+    int32_t prefix_bal[JTB_MAX_ACCOUNTS];
+    for (int i = 0; i < JTB_MAX_ACCOUNTS; ++i) prefix_bal[i] = m->init_balance[i];
+    auto apply = [](int32_t* bal, const int32_t* op, int times) {   // bank transfer record (x, y = amount, z, w)
+        if ((op[0] & 0xff) != JTB_F_TRANSFER || (op[0] & OP_IMPOSSIBLE)) return;
+        bal[op[2]] -= op[1] * times;
+        bal[op[3]] += op[1] * times;
+    };
+    if (bank)
+        for (int64_t gg = base; gg < g; ++gg) {   // every op that returned before the witness is linearized
+            const int32_t* r = &P.rows[(size_t)gg * RW];
+            apply(prefix_bal, r + ROW_EXTRA + r[13] * SW, 1);
+        }
+    std::vector<jtb_final_config> all(keys.size() / KW);
+    for (size_t k = 0; k < all.size(); ++k) {
+        const uint64_t* key = &keys[k * KW];
+        jtb_final_config& c = all[k];
+        std::memset(&c, 0, sizeof c);
+        c.state = (bank || m->kind == JTB_MODEL_SET) ? 0 : (int32_t)(uint32_t)key[0];
+        for (int i = 0; i < JTB_MAX_ACCOUNTS; ++i) c.balances[i] = bank ? prefix_bal[i] : 0;
+        for (int t = 0; t < P.S_pad; ++t) {
+            const int32_t* cell = row + ROW_EXTRA + t * SW;
+            if (cell[0] < 0) continue;
+            const bool is_read = (cell[0] & 0xff) == JTB_F_READ;
+            const int32_t ipos = (bank && !is_read) ? cell[4] : cell[3];
+            const int32_t idx = pos_index[ipos];
+            if ((key[1] >> t) & 1ull) {
+                c.linearized_open_index[c.n_linearized_open++] = idx;
+                if (bank) apply(c.balances, cell, 1);
+            } else {
+                c.pending_index[c.n_pending++] = idx;
+            }
+        }
+        std::sort(c.pending_index, c.pending_index + c.n_pending);
+        std::sort(c.linearized_open_index, c.linearized_open_index + c.n_linearized_open);
+        for (int cc = 0; cc < ncls; ++cc) {
+            const ClassRec& cr = P.classes[cls_base + cc];
+            const int shift = cr.shift_width & 0xff, width = cr.shift_width >> 8;
+            const int count = (int)((key[cr.word] >> shift) & ((1ull << width) - 1));
+            c.n_crashed_linearized += count;
+            if (bank) apply(c.balances, &cr.op.x, count);
+        }
+    }
+    // canonical order: lexicographic over the struct's int32 fields in declaration order (unused entries are 0)
+    std::sort(all.begin(), all.end(), [](const jtb_final_config& a, const jtb_final_config& b) {
+        const int32_t* x = reinterpret_cast<const int32_t*>(&a);
+        const int32_t* y = reinterpret_cast<const int32_t*>(&b);
+        for (size_t i = 0; i < sizeof(jtb_final_config) / 4; ++i)
+            if (x[i] != y[i]) return x[i] < y[i];
+        return false;
+    });
+    const size_t n_out = std::min<size_t>(all.size(), (size_t)std::max(cap, 0));
+    if (n_out) std::memcpy(out, all.data(), n_out * sizeof(jtb_final_config));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 int jtb_check_set_full(jtb_ctx* ctx, const jtb_history* h, int linearizable, jtb_setfull_out* out) {
     if (!ctx) return -1;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    ctx->fc.valid = false;
     return run_set_full(ctx->stream, ctx->ev0, ctx->ev1, h, linearizable, out, ctx->err);
 }
 
@@ -569,6 +707,7 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
     if (!ctx) return -1;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    ctx->fc.valid = false;
     return run_bank_totals(ctx->stream, ctx->ev0, ctx->ev1, h, accounts, total_amount, out, ctx->err);
 }
 
@@ -598,6 +737,7 @@ int jtb_table_bench(jtb_ctx* ctx, uint64_t n_keys, int variant, int rounds, doub
     if (!ctx) return -1;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    ctx->fc.valid = false;
     size_t table_bytes = ctx->opts.table_bytes ? ctx->opts.table_bytes : (size_t)8 << 30;
     uint64_t n_slots = 1;
     while (n_slots * 2 * 16 <= table_bytes) n_slots <<= 1;

@@ -795,4 +795,20 @@ __global__ void table_rehash_kernel(const uint64_t* __restrict__ old_table, uint
     }
 }
 
+// knossos :configs — gathers every visited key whose frontier rank is `rank` (two passes: count, then collect).
+template <int KW>
+__global__ void table_collect_kernel(const uint64_t* __restrict__ table, uint64_t n_slots, uint32_t rank,
+                                     uint64_t* __restrict__ out, unsigned long long cap,
+                                     unsigned long long* __restrict__ counter) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k0 = table[i * KW];
+        if (k0 == 0 || (uint32_t)((k0 >> 32) & RANK_MASK) != rank) continue;
+        const unsigned long long o = atomicAdd(counter, 1ull);
+        if (o < cap) {
+#pragma unroll
+            for (int w = 0; w < KW; ++w) out[o * KW + w] = w == 0 ? (k0 & ~KEY_LOCK) : table[i * KW + w];
+        }
+    }
+}
+
 }  // namespace jtb

@@ -23,7 +23,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
-           "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds", "jtb_prepare_info"]
+           "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds", "jtb_prepare_info",
+           "jtb_final_configs"]
 
 _lib = None
 _lock = threading.Lock()
@@ -66,6 +67,7 @@ def lib() -> C.CDLL:
             L.jtb_last_error.restype = C.c_char_p
             L.jtb_last_error.argtypes = [C.c_void_p]
             L.jtb_check_linearizable.argtypes = [C.c_void_p] * 5
+            L.jtb_final_configs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
             L.jtb_check_set_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
             L.jtb_check_bank_totals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
             L.jtb_table_bench.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
@@ -153,6 +155,18 @@ class Context:
             "lowest_index": res.lowest_index, "highest_index": res.highest_index,
             "seconds": res.seconds_total, "seconds_kernel": res.seconds_kernel,
         }
+
+    def final_configs(self, h: FlatHistory, model: CModel, shard: int = 0, cap: int = 10) -> dict:
+        """knossos' :configs of an INVALID shard (`jtb_final_configs`): call directly after `check_linearizable`
+        on the same history.  Returns {"total": all such configurations, "configs": the first `cap` of them}."""
+        ch = as_c_history(h)
+        buf = (abi.CFinalConfig * max(cap, 1))()
+        total = C.c_int64(0)
+        rc = lib().jtb_final_configs(self._h, C.addressof(ch), C.addressof(model), shard, C.addressof(buf), cap,
+                                     C.addressof(total))
+        if rc != 0:
+            raise NativeError(f"jtb_final_configs rc={rc}: {self._err()}")
+        return {"total": total.value, "configs": abi.final_configs_to_list(buf, min(cap, total.value))}
 
     def stats(self) -> dict:
         out = (C.c_ulonglong * 20)()

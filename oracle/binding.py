@@ -52,6 +52,18 @@ def check_linearizable(h: FlatHistory, model: CModel, algo: int = ALGO_WGL_COMPA
     }
 
 
+def final_configs(h: FlatHistory, model: CModel, shard: int = 0, cap: int = 10, eager_reads: bool = False) -> dict:
+    """Twin of `jtb_final_configs`: knossos' :configs of an INVALID shard; total = -1 when it is not INVALID."""
+    ch = as_c_history(h)
+    buf = (abi.CFinalConfig * max(cap, 1))()
+    total = C.c_int64(0)
+    rc = lib().jtbo_final_configs(C.byref(ch), C.byref(model), 1 | (2 if eager_reads else 0), shard, buf, cap,
+                                  C.byref(total))
+    if rc != 0:
+        raise RuntimeError(lib().jtbo_last_error().decode())
+    return {"total": total.value, "configs": abi.final_configs_to_list(buf, max(0, min(cap, total.value)))}
+
+
 def check_set_full(h: FlatHistory, linearizable: bool = True) -> dict:
     ch = as_c_history(h)
     shards = (abi.CSetFullShard * h.n_shards)()

@@ -50,6 +50,11 @@ class KeySet {
         }
     }
     size_t size() const { return n; }
+    template <class F>
+    void for_each(F f) const {
+        for (size_t i = 0; i < cap; ++i)
+            if (slots[i * W]) f(&slots[i * W]);
+    }
 
   private:
     int W;
@@ -266,6 +271,10 @@ struct WGL {
     const Shard& sh;
     bool compact, canon, eager;
     uint64_t max_configs;
+    // knossos :configs: when set (compact keys only) and the verdict is INVALID, receives every visited key whose
+    // frontier is the witness (W words each), plus the initial configuration when the very first return is stuck
+    std::vector<uint64_t>* final_keys = nullptr;
+    int final_W = 0;
     // eager: "eager reads" reduction (NOT in Knossos; mirrors the device search so that exhaustive config
     // counts can be compared): a consistent read never changes the state, so when some candidate read is
     // consistent with the current config it is linearized immediately and EXCLUSIVELY (no sibling is
@@ -410,6 +419,18 @@ struct WGL {
                 if (stack.empty()) {
                     v.valid = JTB_INVALID;
                     v.witness_ret = max_rj;
+                    if (final_keys && compact) {
+                        final_W = W;
+                        if (max_rj == 0) {   // the initial configuration is never inserted
+                            State s0 = sh.init;
+                            std::fill(crashbits.begin(), crashbits.end(), 0);
+                            make_key(0, 0, s0);
+                            final_keys->insert(final_keys->end(), key.begin(), key.end());
+                        }
+                        cache.for_each([&](const uint64_t* k) {
+                            if ((int)((k[0] >> 32) & 0x1fffffffu) == max_rj) final_keys->insert(final_keys->end(), k, k + W);
+                        });
+                    }
                     return v;
                 }
                 Frame fr = stack.back();
@@ -456,6 +477,80 @@ thread_local std::string g_err;
 extern "C" {
 
 const char* jtbo_last_error(void) { return g_err.c_str(); }
+
+// knossos :configs restated (the twin of jtb_final_configs, include/jtb_check.h): the configurations of an INVALID
+// shard whose first un-linearized return is the witness, decoded and in the same canonical order.
+// canon_info as in jtbo_check_linearizable (bit 0 is required: keys identify crashed ops by class counts there).
+// Returns 0 and *n_total >= 0; *n_total = -1 when the shard is not INVALID.
+int jtbo_final_configs(const jtb_history* h, const jtb_model* m, int canon_info, int32_t shard, jtb_final_config* out,
+                       int32_t cap, int64_t* n_total) {
+    try {
+        Shard sh = preprocess(h, shard, m);
+        WGL w(sh, true, true, 0, (canon_info & 2) != 0);
+        std::vector<uint64_t> keys;
+        w.final_keys = &keys;
+        Verdict v = w.run();
+        if (v.valid != JTB_INVALID) { *n_total = -1; return 0; }
+        const int W = w.final_W;
+        const int g = v.witness_ret;
+        const Op& wit = sh.ops[sh.rets[g]];
+        const bool bank = m->kind == JTB_MODEL_BANK;
+        std::vector<int> rank(sh.ops.size(), -1), crashed_ops;
+        for (int j = 0; j < (int)sh.rets.size(); ++j) rank[sh.rets[j]] = j;
+        for (int i = 0; i < (int)sh.ops.size(); ++i)
+            if (sh.ops[i].crashed) crashed_ops.push_back(i);
+        auto apply = [&](int32_t* bal, const Op& o) {
+            if (o.f != JTB_F_TRANSFER || o.impossible) return;
+            const int d = acct_slot(m, o.b), c = acct_slot(m, o.c);
+            if (d < 0 || c < 0) return;
+            bal[d] -= o.a;
+            bal[c] += o.a;
+        };
+        int32_t prefix[JTB_MAX_ACCOUNTS];
+        for (int i = 0; i < JTB_MAX_ACCOUNTS; ++i) prefix[i] = sh.init.bal[i];
+        if (bank)
+            for (int j = 0; j < g; ++j) apply(prefix, sh.ops[sh.rets[j]]);
+        std::vector<jtb_final_config> all(keys.size() / W);
+        for (size_t k = 0; k < all.size(); ++k) {
+            const uint64_t* key = &keys[k * W];
+            jtb_final_config& c = all[k];
+            std::memset(&c, 0, sizeof c);
+            c.state = (bank || m->kind == JTB_MODEL_SET) ? 0 : (int32_t)(uint32_t)key[0];
+            for (int i = 0; i < JTB_MAX_ACCOUNTS; ++i) c.balances[i] = bank ? prefix[i] : 0;
+            for (int i = 0; i < (int)sh.ops.size(); ++i) {
+                const Op& o = sh.ops[i];
+                if (o.crashed || o.inv_pos > wit.ret_pos || rank[i] < g) continue;   // open at the witness' return
+                if ((key[1] >> o.slot) & 1ull) {
+                    c.linearized_open_index[c.n_linearized_open++] = o.inv_index;
+                    if (bank) apply(c.balances, o);
+                } else {
+                    c.pending_index[c.n_pending++] = o.inv_index;
+                }
+            }
+            std::sort(c.pending_index, c.pending_index + c.n_pending);
+            std::sort(c.linearized_open_index, c.linearized_open_index + c.n_linearized_open);
+            for (size_t b = 0; b < crashed_ops.size(); ++b)
+                if ((key[2 + (b >> 6)] >> (b & 63)) & 1ull) {
+                    c.n_crashed_linearized++;
+                    if (bank) apply(c.balances, sh.ops[crashed_ops[b]]);
+                }
+        }
+        std::sort(all.begin(), all.end(), [](const jtb_final_config& a, const jtb_final_config& b) {
+            const int32_t* x = reinterpret_cast<const int32_t*>(&a);
+            const int32_t* y = reinterpret_cast<const int32_t*>(&b);
+            for (size_t i = 0; i < sizeof(jtb_final_config) / 4; ++i)
+                if (x[i] != y[i]) return x[i] < y[i];
+            return false;
+        });
+        *n_total = (int64_t)all.size();
+        const size_t n_out = std::min<size_t>(all.size(), (size_t)std::max(cap, 0));
+        if (n_out) std::memcpy(out, all.data(), n_out * sizeof(jtb_final_config));
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 
 // algo: 0 brute, 1 linear, 2 wgl (full-bitset cache), 3 wgl compact (timed baseline)
 // canon_info: bit 0 = linearize crashed ops of one class (same f/value) in invocation order only;

@@ -42,7 +42,7 @@ def test_no_cpu_fallback_without_device():
 def test_struct_sizes_match_the_compiled_library():
     lib = native.lib()
     images = [history.CHistory, history.CModel, abi.COpts, abi.CLinShard, abi.CLinResult, abi.CSetFullShard,
-              abi.CSetFullOut, abi.CBankResult]
+              abi.CSetFullOut, abi.CBankResult, abi.CFinalConfig]
     for which, img in enumerate(images):
         assert lib.jtb_struct_size(which) == ctypes.sizeof(img), img.__name__
     assert lib.jtb_struct_size(99) == -1

@@ -406,3 +406,62 @@ def test_scouts_do_not_disturb_exhaustive_counts_or_growth(oracle_mod, monkeypat
     same_verdict(g, o)
     assert g["configs"] == o["configs"], (st, o["configs"])
     assert st["scouts"] == 4 and st["scout_decided"] == 0, st
+
+
+FINAL_CONFIG_CASES = [
+    ("register", (1, 4), dict(n_ops=400, n_clients=6, p_info=0.02, n_values=30, stale_read=True, stale_by=3)),
+    ("cas-register", (1,), dict(n_ops=1000, n_clients=16, n_values=30, stale_read=True)),
+    ("bank", (1, 3), dict(n_ops=1500, n_clients=10, p_info=0.03, stale_read=True, tau_think_ns=4e6)),
+    ("register", (2, 3), dict(n_ops=3000, n_clients=4, n_values=30, stale_read=True, n_keys=8)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,seeds,kw", FINAL_CONFIG_CASES, ids=[f"{m}-{k['n_ops']}" for m, _s, k in FINAL_CONFIG_CASES])
+def test_final_configs_match_the_oracle(oracle_mod, model, seeds, kw):
+    """knossos' :configs: every visited configuration stuck at the witness, read back from the
+    visited table in HBM and decoded, equals the oracle's list config for config (state, balances, pending ops,
+    linearized-but-open ops, crashed ops consumed), in both search modes, for single- and multi-key histories."""
+    from jepsen_tigerbeetle_b200 import native
+    m = model_for(model)
+    checked = 0
+    for seed in seeds:
+        h = synth.generate(synth.SynthSpec(model, seed=seed, **kw))
+        for eager in (True, False):
+            o = oracle_mod.check_linearizable(h, m, 3, eager_reads=eager, max_configs=30_000_000)
+            assert o["valid"] == H.INVALID
+            with native.Context(eager_reads=eager) as ctx:
+                g = ctx.check_linearizable(h, m)
+                same_verdict(g, o)
+                for k, s in enumerate(o["shards"]):
+                    if s["valid"] != H.INVALID:
+                        with pytest.raises(native.NativeError):
+                            ctx.final_configs(h, m, shard=k)
+                        continue
+                    fg = ctx.final_configs(h, m, shard=k, cap=20000)
+                    fo = oracle_mod.final_configs(h, m, shard=k, cap=100000, eager_reads=eager)
+                    assert fg["total"] == fo["total"] >= 1, (seed, eager, k)
+                    assert fg["configs"] == fo["configs"], (seed, eager, k)
+                    assert ctx.final_configs(h, m, shard=k, cap=3)["configs"] == fo["configs"][:3]
+                    checked += 1
+                if model == "bank":   # any other call on the context invalidates the table of the last search
+                    ctx.check_bank_totals(h, m)
+                    with pytest.raises(native.NativeError):
+                        ctx.final_configs(h, m, shard=0)
+    assert checked >= 2
+
+
+@pytest.mark.gpu
+def test_linearizable_checker_reports_configs(gpu_ctx):
+    """The Checker-protocol mirror returns knossos' :configs for an invalid history (first 10, like jepsen)."""
+    from jepsen_tigerbeetle_b200 import checker
+
+    def op(p, t, f, v, i):
+        return {"process": p, "type": t, "f": f, "value": v, "index": i, "time": i * 1000}
+    hist = [op(0, "invoke", "write", 1, 0), op(0, "ok", "write", 1, 1), op(1, "invoke", "write", 3, 2),
+            op(0, "invoke", "read", None, 3), op(0, "ok", "read", 2, 4), op(1, "ok", "write", 3, 5)]
+    r = checker.linearizable({"model": "register"}).check({}, hist, {})
+    assert r["valid?"] is False and r["op"] == {"index": 4} and r["configs-total"] == 2
+    assert r["configs"] == [
+        {"model": 1, "pending": [{"index": 2}, {"index": 3}], "linearized-open": [], "crashed-linearized": 0},
+        {"model": 3, "pending": [{"index": 3}], "linearized-open": [{"index": 2}], "crashed-linearized": 0}]
