@@ -12,7 +12,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 MODEL = {"register": H.MODEL_REGISTER, "cas-register": H.MODEL_CAS_REGISTER, "set": H.MODEL_SET, "bank": H.MODEL_BANK}
 ctxs = {True: native.Context(eager_reads=True), False: native.Context(eager_reads=False)}
 t0 = time.time()
-n = n_invalid = n_skipped = n_multi = 0
+n = n_invalid = n_skipped = n_multi = n_final = 0
 bad = []
 while time.time() - t0 < budget_s:
     model = list(MODEL)[int(rng.integers(0, 4))]
@@ -45,10 +45,15 @@ while time.time() - t0 < budget_s:
         n_invalid += 1
         if h.n_shards == 1:
             ok = ok and g["configs"] == o["configs"]
+            if g["valid"] == H.INVALID:   # knossos :configs, config for config
+                fg = ctxs[eager].final_configs(h, m, 0, 50)
+                fo = oracle.final_configs(h, m, 0, 50, eager_reads=eager)
+                ok = ok and fg == fo
+                n_final += 1
     if not ok:
         bad.append({"spec": str(spec), "eager": eager, "gpu": {k: g[k] for k in ("valid", "configs")},
                     "gpu_shards": g["shards"][:4], "cpu": {k: o[k] for k in ("valid", "configs")}, "cpu_shards": o["shards"][:4]})
         print("MISMATCH", bad[-1], flush=True)
-print(json.dumps({"cases": n, "invalid": n_invalid, "multi_key": n_multi, "skipped": n_skipped, "mismatches": len(bad),
+print(json.dumps({"cases": n, "invalid": n_invalid, "multi_key": n_multi, "skipped": n_skipped, "final_config_checks": n_final, "mismatches": len(bad),
                   "seconds": round(time.time() - t0, 1)}))
 sys.exit(1 if bad else 0)
