@@ -10,6 +10,8 @@
 //   lifo       global depth-first-ish stack (newest W)
 //   rank       best-first by frontier rank (furthest first), newest first inside a rank
 //   rank-crash best-first by rank, then FEWEST crashed ops consumed (dominating configs first)
+//   bucket:S   what a GPU queue can afford: rank buckets of 2^S ranks, 16 sub-buckets by crashed ops consumed
+//              relative to the bucket's running minimum (computed when the config is pushed), LIFO inside
 // Register / cas-register only.  Build: g++ -O2 -std=c++17 -I../../include -I../../oracle policy_sim.cpp
 #include <algorithm>
 #include <cstdio>
@@ -33,13 +35,16 @@ struct Cfg {
     std::vector<uint8_t> cnt;   // crashed-class counts
     int crashed_used;
     uint64_t seq;
+    int pb = 0, ps = 0;   // bucket / sub-bucket, fixed at push time (policy bucket:S)
+    bool must_obs = false;   // JTB_SIM_LAZY=1: the last op was a crashed one, the next must observe the state
 };
 struct KeyHash {
     size_t operator()(const std::string& s) const { return std::hash<std::string>()(s); }
 };
 static std::string key_of(const Cfg& c) {
     std::string k(16 + c.cnt.size(), '\0');
-    std::memcpy(&k[0], &c.rj, 4);
+    const int rj_flag = c.rj | (c.must_obs ? 1 << 30 : 0);
+    std::memcpy(&k[0], &rj_flag, 4);
     std::memcpy(&k[4], &c.reg, 4);
     std::memcpy(&k[8], &c.mask, 8);
     if (!c.cnt.empty()) std::memcpy(&k[16], c.cnt.data(), c.cnt.size());
@@ -51,6 +56,7 @@ struct Sim {
     std::vector<std::vector<int>> open_at;   // completed ops open at each return rank
     std::vector<int> rank;
     bool eager = true;
+    bool lazy = std::getenv("JTB_SIM_LAZY") != nullptr;   // "lazy crashed ops" normal form
 
     explicit Sim(Shard s) : sh(std::move(s)) {
         const int R = (int)sh.rets.size();
@@ -73,8 +79,11 @@ struct Sim {
         const int rp = sh.ops[sh.rets[c.rj]].ret_pos;
         auto lin = [&](int i, Cfg n) {
             const Op& o = sh.ops[i];
+            if (lazy && n.must_obs && o.f == JTB_F_WRITE) return false;
             State st; st.reg = n.reg;
             if (!step(sh, o, st, nullptr)) return false;
+            if (lazy && o.crashed && st.reg == n.reg) return false;
+            n.must_obs = lazy && o.crashed;
             n.reg = st.reg;
             if (o.crashed) { n.cnt[o.cls]++; n.crashed_used++; }
             else if (sh.rets[n.rj] == i) {
@@ -134,7 +143,11 @@ int main(int argc, char** argv) {
     const size_t W = (size_t)std::atoll(argv[3]);
     const uint64_t max_configs = (uint64_t)std::atoll(argv[4]);
 
+    const bool bucketed = policy.rfind("bucket:", 0) == 0;
+    const int shift = bucketed ? std::atoi(policy.c_str() + 7) : 0;
+    std::vector<int> min_crashed((sim.sh.rets.size() >> shift) + 2, 1 << 30);
     auto prio = [&](const Cfg& x) -> std::tuple<long long, long long, long long> {   // larger = expanded earlier
+        if (bucketed) return {x.pb, -x.ps, (long long)x.seq};
         if (policy == "fifo") return {0, 0, -(long long)x.seq};
         if (policy == "lifo") return {0, 0, (long long)x.seq};
         if (policy == "rank") return {x.rj, 0, (long long)x.seq};
@@ -160,6 +173,12 @@ int main(int argc, char** argv) {
                     ++configs;
                     max_rj = std::max(max_rj, k.rj);
                     k.seq = seq++;
+                    if (bucketed) {
+                        k.pb = k.rj >> shift;
+                        int& mc = min_crashed[k.pb];
+                        mc = std::min(mc, k.crashed_used);
+                        k.ps = std::min(15, k.crashed_used - mc);
+                    }
                     pq.push(std::move(k));
                 }
         }
