@@ -94,6 +94,17 @@
 
 (defonce ^:private ctx (delay (Native/create 0)))   ; one context per JVM; calls on it are serialised
 
+(defn- decode-configs
+  "int[] from Native/finalConfigs -> [{:model state-or-balances :pending [{:index i}..] ...}]"
+  [^ints xs]
+  (for [off (range 1 (alength xs) 140)
+        :let [rec  (vec (java.util.Arrays/copyOfRange xs (int off) (int (+ off 140))))
+              np   (rec 9) nl (rec 10)]]
+    {:model             {:register (rec 0) :balances (subvec rec 1 9)}
+     :pending           (mapv #(hash-map :index %) (subvec rec 12 (+ 12 np)))
+     :linearized-open   (mapv #(hash-map :index %) (subvec rec 76 (+ 76 nl)))
+     :crashed-linearized (rec 11)}))
+
 (defn linearizable
   "Replacement for (checker/linearizable {:model m}); m in #{:register :cas-register :set :bank}."
   [{:keys [model]}]
@@ -107,7 +118,10 @@
         ;; res: long[] {valid witness previous-ok cause configs probes} per shard, shard-major
         (let [[valid witness prev cause-code configs] (take 5 res)]
           (cond-> {:valid? (verdict valid) :analyzer :wgl-gpu :configs-explored configs}
-            (= 2 valid) (assoc :op {:index witness} :previous-ok (when (<= 0 prev) {:index prev}))
+            (= 2 valid) (assoc :op {:index witness} :previous-ok (when (<= 0 prev) {:index prev})
+                               ;; knossos' :configs, first 10 like jepsen.checker/linearizable keeps them:
+                               ;; int[] {total, then 140 ints per config in jtb_final_config field order}
+                               :configs (decode-configs (Native/finalConfigs @ctx h (name model) 0 10)))
             (= 1 valid) (assoc :cause (cause cause-code))))))))
 
 (defn set-full

@@ -92,5 +92,21 @@ JNIEXPORT jlongArray JNICALL Java_jtb_Native_checkLinearizable0(
     free(shards);
     return out;
 }
+/* int[] finalConfigs0(long ctx, <the same history and model arguments as checkLinearizable0>, int shard, int cap)
+ * knossos' :configs of an INVALID shard (jtb_final_configs): same pin -> fill jtb_history -> call -> unpin pattern;
+ * call it directly after checkLinearizable0 on the same arrays.  Returns the total number of such configurations
+ * followed by min(cap, total) records of sizeof(jtb_final_config)/4 = 140 ints each, in the struct's field order:
+ * state, balances[8], n_pending, n_linearized_open, n_crashed_linearized, pending_index[64],
+ * linearized_open_index[64]. */
+static jintArray final_configs_result(JNIEnv* env, const jtb_final_config* buf, int32_t cap, int64_t total) {
+    const jsize rec = (jsize)(sizeof(jtb_final_config) / 4);
+    const jsize n = (jsize)(total < cap ? total : cap);
+    jintArray out = (*env)->NewIntArray(env, 1 + n * rec);
+    jint t = (jint)total;
+    (*env)->SetIntArrayRegion(env, out, 0, 1, &t);
+    if (n) (*env)->SetIntArrayRegion(env, out, 1, n * rec, (const jint*)buf);
+    return out;
+}
+
 /* checkSetFull0 / checkBankTotals0 follow the same pin -> fill jtb_history -> call -> unpin pattern
  * around jtb_check_set_full / jtb_check_bank_totals and return their result structs as long[]. */
