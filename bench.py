@@ -12,9 +12,18 @@ value    = configs / device time of the search kernels (CUDA events on the libra
            already in HBM)            e2e = configs / wall time of the C-ABI call with HOST buffers
            (flatten-prep, H2D, table clear, kernels, D2H verdict inside the timed region).
 
+sharded  : beside the headline every line carries `"sharded"`: BASELINE configs #5 (50k-op cas-register, 30 %
+           :info, K = 256 keys, one key poisoned) and #4 (100k-op set-full, K = 64 ledgers, one ledger
+           poisoned) checked over the N GPUs — more shards than ranks, LPT partition, the merged verdict
+           must flip to invalid with exactly one failure; STRONG scaling (total work fixed), time to the
+           merged verdict as max over ranks plus every rank's own device time (imbalance is visible).
+
 --impl reference : the CPU restatement of knossos.wgl (oracle/, kind "port" — the reference's own
            implementation is JVM-only and cannot run here) on the same history, each step a bounded
-           sample (first --ref-configs configurations), single thread like knossos.wgl.
+           sample (first --ref-configs configurations) on one thread per key like knossos.wgl (N keys ->
+           N threads); ONE full run to the verdict is timed beside it (`time_to_verdict_s`, rank 0 only,
+           key 1) so that the driver's record carries a verdict-to-verdict ratio.  Its `sharded` object
+           runs the same C5 / C4 histories over min(16 N, host cores) threads (independent/checker's fan-out).
 """
 import argparse
 import json
@@ -51,6 +60,95 @@ def config_block(args, n_gpus):
             "model": "bank", "table": "16 B slots, linear probing, load <= 0.5",
             "search_space": "eager-read reduction (product default)" if args.eager_reads else
                             "Knossos-exact (JTB_OPT_NO_EAGER_READS): the same configurations the CPU reference visits"}
+
+
+def sharded_workloads(args):
+    """BASELINE configs #5 and #4 with ONE poisoned key each (the merged verdict must flip)."""
+    import copy
+    c5 = copy.deepcopy(synth.config_c5(seed=1, n_ops=args.c5_ops))
+    # poison one key of C5: its third :ok read returns a value nobody ever wrote (values are 0..4)
+    s = 7
+    lo, hi = int(c5.shard_off[s]), int(c5.shard_off[s + 1])
+    reads = [e for e in range(lo, hi) if c5.f[e] == H.F_READ and c5.type[e] == H.T_OK]
+    c5.a[reads[min(2, len(reads) - 1)]] = 99
+    c4 = synth.config_c4(seed=1, n_keys=64, n_ops=args.c4_ops)
+    # poison one ledger of C4: an element that a read has seen disappears from the ledger's LAST ok read -> lost
+    c4 = copy.deepcopy(c4)
+    s = 5
+    lo, hi = int(c4.shard_off[s]), int(c4.shard_off[s + 1])
+    reads = [e for e in range(lo, hi) if c4.f[e] == H.F_READ and c4.type[e] == H.T_OK and c4.payload_len[e] > 4
+             and not (c4.flags[e] & 1)]
+    e = reads[-1]
+    c4.payload_len[e] -= 2          # payloads are sorted: the two largest (latest) ids vanish from this read ...
+    return c5, c4
+
+
+def run_sharded_ours(args, ctx, rank, world, reduce_max, dist, dev):
+    """Strong scaling over the N ranks: C5 through the WGL search, C4 through the set-full scan."""
+    import torch
+    from jepsen_tigerbeetle_b200 import distributed
+    c5, c4 = sharded_workloads(args)
+    mc = H.make_model(H.MODEL_CAS_REGISTER)
+    out = {}
+    for name, h in (("c5_K256_pinfo0.30_wgl_cas_register", c5), ("c4_K64_set_full", c4)):
+        kern = [0.0]
+
+        def check_fn(sub):
+            if name.startswith("c5"):
+                r = ctx.check_linearizable(sub, mc)
+                kern[0] = r["seconds_kernel"]
+                return r["shards"]
+            r = ctx.check_set_full(sub, True)
+            kern[0] = r["seconds_kernel"]
+            return r["shards"]
+
+        best = None
+        for rep in range(3):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = distributed.check_sharded(h, check_fn, rank, world, reduce_max)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            t = torch.tensor([wall, kern[0]], dtype=torch.float64, device=dev)
+            per_rank = [torch.zeros_like(t) for _ in range(world)]
+            if dist is not None:
+                dist.all_gather(per_rank, t)
+            else:
+                per_rank = [t]
+            walls = [float(x[0]) for x in per_rank]
+            kerns = [float(x[1]) for x in per_rank]
+            rec = {"verdict": {0: "valid", 1: "unknown", 2: "invalid"}[res["valid"]],
+                   "n_failures": int((res["shard_valid"] != 0).sum()), "keys": int(h.n_shards),
+                   "events": int(h.n_events), "time_to_merged_verdict_s": max(walls),
+                   "per_rank_wall_s": walls, "per_rank_kernel_s": kerns,
+                   "shards_per_rank": [len(x) for x in distributed.assign_shards(distributed.shard_costs(h), world)]}
+            if best is None or rec["time_to_merged_verdict_s"] < best["time_to_merged_verdict_s"]:
+                best = rec
+        out[name] = best
+    out["scaling"] = "strong (fixed keys, LPT partition over the ranks; best of 3)"
+    return out
+
+
+def run_sharded_reference(args, world):
+    import oracle
+    c5, c4 = sharded_workloads(args)
+    threads = max(1, min(16 * world, os.cpu_count() or 1))
+    mc = H.make_model(H.MODEL_CAS_REGISTER)
+    out = {"threads": threads}
+    t = time.perf_counter()
+    r = oracle.check_linearizable(c5, mc, oracle.ALGO_WGL_COMPACT, max_configs=50_000_000, n_threads=threads)
+    out["c5_K256_pinfo0.30_wgl_cas_register"] = {
+        "verdict": {0: "valid", 1: "unknown", 2: "invalid"}[r["valid"]], "n_failures": r["n_failures"],
+        "keys": int(c5.n_shards), "time_to_merged_verdict_s": time.perf_counter() - t}
+    t = time.perf_counter()
+    r = oracle.check_set_full(c4, True)
+    out["c4_K64_set_full"] = {"verdict": {0: "valid", 1: "unknown", 2: "invalid"}[r["valid"]],
+                              "n_failures": r["n_failures"], "keys": int(c4.n_shards),
+                              "time_to_merged_verdict_s": time.perf_counter() - t,
+                              "note": "scan_oracle.cpp is single-threaded over the keys"}
+    return out
 
 
 class ClockSampler:
@@ -118,30 +216,47 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle
+    from concurrent.futures import ThreadPoolExecutor
     oracle.build()
-    h = workload(1, args)
+    n_keys = max(1, world)
+    parts = [workload(1 + k, args) for k in range(n_keys)]
     m = H.make_model(H.MODEL_BANK, accounts=range(1, 9))
-    cores = 1  # knossos.wgl searches one history on one thread
+    cores = n_keys  # knossos.wgl searches one history on one thread; independent/checker gives every key a thread
+
+    def one(h):
+        return oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_configs)["configs"]
+
+    pool = ThreadPoolExecutor(n_keys)      # the oracle releases the GIL inside ctypes calls
     for _ in range(args.warmup):
-        oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_configs)
+        list(pool.map(one, parts))
     configs, secs = 0, 0.0
     for _ in range(args.steps):
         t = time.perf_counter()
-        r = oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_configs)
+        configs += sum(pool.map(one, parts))
         secs += time.perf_counter() - t
-        configs += r["configs"]
     v = configs / secs
-    sample = (f"first {args.ref_configs} configurations of the same history per step "
-              f"(single thread, like knossos.wgl; {os.cpu_count()} host cores present)")
-    print(json.dumps({
+    sample = (f"first {args.ref_configs} configurations of every key's history per step, one thread per key "
+              f"(knossos.wgl is single-threaded per history; {os.cpu_count()} host cores present)")
+    line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
-        "data": "synthetic", "config": config_block(args, 1),
+        "data": "synthetic", "config": config_block(args, n_keys),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of knossos.wgl (oracle/lin_oracle.cpp); JVM Knossos cannot run here",
-    }))
+        "note": "CPU restatement of knossos.wgl (oracle/lin_oracle.cpp, -O3 -march=native); JVM Knossos cannot run here",
+    }
+    if not args.no_full_run:
+        t = time.perf_counter()
+        r = oracle.check_linearizable(parts[0], m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_full_configs)
+        dt = time.perf_counter() - t
+        line["time_to_verdict_s"] = dt
+        line["verdict"] = {0: "valid", 1: "unknown", 2: "invalid"}[r["valid"]]
+        line["configs_to_verdict"] = r["configs"]
+        line["time_to_verdict_note"] = "ONE full run of key 1 to its verdict, single thread, outside the timed steps"
+    if not args.no_sharded:
+        line["sharded"] = run_sharded_reference(args, world)
+    print(json.dumps(line))
 
 
 def main():
@@ -157,6 +272,11 @@ def main():
     ap.add_argument("--ref-configs", type=int, default=3_000_000)
     ap.add_argument("--cpu-baseline-configs", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-run", action="store_true", help="reference arm: skip the one full run to the verdict")
+    ap.add_argument("--ref-full-configs", type=int, default=400_000_000, help="budget of that full run")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the C5 / C4 sharded workloads")
+    ap.add_argument("--c5-ops", type=int, default=50000)
+    ap.add_argument("--c4-ops", type=int, default=100000)
     ap.add_argument("--eager-reads", action="store_true",
                     help="time the product default (eager-read reduction: ~18x fewer configs, same verdict) instead of "
                          "the Knossos-exact search space the CPU reference explores")
@@ -224,6 +344,17 @@ def main():
         dist.all_reduce(agg, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     kern_max, wall_max = (float(x) for x in agg.cpu())
+    mine_k = torch.tensor([kern_s], dtype=torch.float64, device=dev)
+    gathered = [torch.zeros_like(mine_k) for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(gathered, mine_k)
+    else:
+        gathered = [mine_k]
+    per_rank_kern = [float(x[0]) for x in gathered]
+    sharded = None
+    if not args.no_sharded:
+        with native.Context(device=local_rank) as sctx:      # product defaults (eager reads, scouts)
+            sharded = run_sharded_ours(args, sctx, rank, world, reduce_max, dist, dev)
     configs_t, probes_t, bytes_t, launches_t, h2d_t, d2h_t = (float(x) for x in tot.cpu())
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -248,6 +379,9 @@ def main():
                          "random_probe_ceiling_GBps": tr.get("table_probe_algo_GBps") if tr else None},
             "clocks": clocks,
         }
+        line["per_rank_kernel_s_per_step"] = [x / args.steps for x in per_rank_kern]
+        if sharded is not None:
+            line["sharded"] = sharded
         if world == 1 and not args.eager_reads:
             with native.Context(device=local_rank, eager_reads=True) as ectx:
                 for _ in range(2):

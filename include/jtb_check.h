@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define JTB_ABI_VERSION 1
+#define JTB_ABI_VERSION 2
 
 /* ---- verdict lattice (jepsen.checker/merge-valid) ------------------------------------------- */
 #define JTB_VALID   0
@@ -199,8 +199,13 @@ typedef struct jtb_setfull_out {
 #define JTB_BANK_NEGATIVE_VALUE 4
 
 typedef struct jtb_bank_result {
-    int32_t valid;
-    int32_t reserved0;
+    int32_t valid;                 /* JTB_UNKNOWN when reference_throws (what check-safe makes of the exception) */
+    int32_t reference_throws;      /* 1: the reference checker THROWS on this history — err-badness divides by
+                                      (:total-amount test) (tests/ledger.clj:122-123), the default is 0
+                                      (tests/ledger.clj:356), and util/max-by calls it as soon as one error type has
+                                      >= 2 :wrong-total errors; jepsen's check-safe turns that into
+                                      {:valid? :unknown}.  All counts / firsts / lasts below are still filled;
+                                      :worst then ranks :wrong-total errors by |total - total-amount|.            */
     int64_t read_count;            /* :read-count  */
     int64_t error_count;           /* :error-count */
     int32_t first_error_index;     /* :index of (:op :first-error), -1                                 */
@@ -264,6 +269,31 @@ int jtb_check_set_full(jtb_ctx* ctx, const jtb_history* h, int linearizable, jtb
 int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* accounts,
                           int64_t total_amount, jtb_bank_result* out);
 
+/* ---- multi-GPU fan-out inside the library (SURVEY §8(b) `n_gpus`, §8(e)) ----------------------------------- *
+ * What `independent/checker` (set_full.clj:155) does over JVM threads, done over the GPUs of one box for a host
+ * that is a single process (a JVM through JNI): the shards (independent keys) of the history are partitioned over
+ * `n_gpus` devices (longest-processing-time-first on events^2), every device checks its share through its own
+ * context on its own host thread, and the per-shard (verdict, witness, previous-ok) vectors are merged with ONE
+ * ncclAllReduce(ncclMax) over int32[3 * n_shards] (ncclCommInitAll inside the library; NCCL is dlopen'ed at
+ * jtb_multi_create, libjtb_check.so itself has no link-time dependency on it).  No configuration ever crosses GPUs:
+ * linearizability is local (Herlihy-Wing), so the verdict lattice 0 < 1 < 2 under MAX is all that has to travel.
+ * A history with ONE shard runs on the first device (it does not shard: SURVEY §8(e) "replicas only").
+ * opts->device is ignored (devices 0 .. n_gpus-1); n_gpus <= 0 means every visible device.                     */
+typedef struct jtb_multi jtb_multi;
+jtb_multi*  jtb_multi_create(const jtb_opts* opts, int n_gpus);   /* NULL on failure (see jtb_multi_create_error) */
+const char* jtb_multi_create_error(void);                          /* why the last jtb_multi_create returned NULL   */
+void        jtb_multi_destroy(jtb_multi* mg);
+int         jtb_multi_n_gpus(const jtb_multi* mg);
+const char* jtb_multi_last_error(const jtb_multi* mg);
+/* same contract as jtb_check_linearizable; out->seconds_kernel = max over devices; device_of_shard (may be NULL)
+ * receives the device each shard was checked on */
+int jtb_multi_check_linearizable(jtb_multi* mg, const jtb_history* h, const jtb_model* m,
+                                 jtb_lin_shard* shards, jtb_lin_result* out, int32_t* device_of_shard);
+/* same contract as jtb_check_set_full; only the per-shard structs are merged (the optional per-element and
+ * suspect-read detail of `out` must be unset: elem_capacity == suspect_capacity == missing_capacity == 0) */
+int jtb_multi_check_set_full(jtb_multi* mg, const jtb_history* h, int linearizable, jtb_setfull_out* out,
+                             int32_t* device_of_shard);
+
 /* ---- diagnostics: counters of the last jtb_check_linearizable call ------------------------------ *
  * out[0..11] = configs, probes, expansions, ring tail, ring head, idle polls, max probe length,
  * table slots, grid CTAs, ring entries, search launches (pause/resume growth + 1), kernel microseconds,
@@ -283,6 +313,14 @@ double jtb_prepare_info(const jtb_history* h, const jtb_model* m, long long info
  * seconds for insert and probe phases.  variant selects the probe path.          */
 int jtb_table_bench(jtb_ctx* ctx, uint64_t n_keys, int variant, int rounds,
                     double* insert_seconds, double* probe_seconds, uint64_t* found);
+
+/* ---- the memory system under a hash probe: random 16 B gathers as a function of the footprint ------------------ *
+ * Every thread issues `iters` rounds of `in_flight` (1, 2, 4, 8, 16) independent random 16 B loads (the search
+ * kernel's ld.global.cg.v2.u64 probe; wide = 2: both halves of the 32 B sector) over a table of table_bytes
+ * (rounded down to a power of two), ctas_per_sm x 256 threads per SM.  Returns the best of `rounds` timings and the
+ * number of 16 B-slot probes issued.  profiles/ holds the sweep 64 MiB .. 16 GiB.               */
+int jtb_gather_bench(jtb_ctx* ctx, uint64_t table_bytes, int in_flight, int wide, uint32_t iters, int ctas_per_sm,
+                     int rounds, double* seconds, uint64_t* n_probes);
 
 #ifdef __cplusplus
 }

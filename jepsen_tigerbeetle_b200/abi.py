@@ -5,7 +5,7 @@ import ctypes as C
 
 from .history import MAX_ACCOUNTS
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OPT_NO_EAGER_READS = 1
 OPT_NO_SCOUTS = 2
 
@@ -71,7 +71,7 @@ class CSetFullOut(C.Structure):
 
 
 class CBankResult(C.Structure):
-    _fields_ = [("valid", C.c_int32), ("reserved0", C.c_int32), ("read_count", C.c_int64),
+    _fields_ = [("valid", C.c_int32), ("reference_throws", C.c_int32), ("read_count", C.c_int64),
                 ("error_count", C.c_int64), ("first_error_index", C.c_int32),
                 ("first_error_type", C.c_int32), ("count_by_type", C.c_int64 * 5),
                 ("first_index_by_type", C.c_int32 * 5), ("last_index_by_type", C.c_int32 * 5),

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "jtb_wgl.cuh"
+#include "jtb_search.cuh"
 #include "jtb_scout.cuh"
 #include "jtb_scans.cuh"
 #include "jtb_table_bench.cuh"
@@ -98,6 +99,33 @@ int launch_wgl(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t sm
                          : launch_wgl_b<MODEL, KW, JTB_CTAS_EXACT, false>(ctx, p, neg_ok, grid, smem);
 }
 
+// the thread-per-configuration kernel (jtb_search.cuh)
+template <int MODEL, int KW>
+int launch_tpc(jtb_ctx* ctx, const WglParams& p, int neg_ok, int grid, size_t smem) {
+    if (p.eager_reads) {
+        auto k = wgl_tpc_kernel<MODEL, KW, true>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, TPC_THREADS, smem, ctx->stream>>>(p, neg_ok);
+    } else {
+        auto k = wgl_tpc_kernel<MODEL, KW, false>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, TPC_THREADS, smem, ctx->stream>>>(p, neg_ok);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int MODEL>
+int launch_tpc_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid, size_t smem) {
+    switch (kw) {
+    case 2: return launch_tpc<MODEL, 2>(ctx, p, neg_ok, grid, smem);
+    case 4: return launch_tpc<MODEL, 4>(ctx, p, neg_ok, grid, smem);
+    case 8: return launch_tpc<MODEL, 8>(ctx, p, neg_ok, grid, smem);
+    }
+    ctx->err = "unsupported key width";
+    return -1;
+}
+
 template <int MODEL>
 int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid, size_t smem, int ctas_per_sm) {
     switch (kw) {
@@ -140,8 +168,10 @@ int preload(jtb_ctx* ctx, K kernel) {
 template <int MODEL, int KW>
 int preload_search(jtb_ctx* ctx, bool eager) {
     constexpr int EW = KW + (MODEL == JTB_MODEL_BANK ? 4 : 0);
-    int rc = eager ? (preload(ctx, wgl_search_kernel<MODEL, KW, JTB_CTAS_EAGER, true>) | preload(ctx, wgl_scout_kernel<MODEL, KW, true>))
-                   : (preload(ctx, wgl_search_kernel<MODEL, KW, JTB_CTAS_EXACT, false>) | preload(ctx, wgl_scout_kernel<MODEL, KW, false>));
+    int rc = eager ? (preload(ctx, wgl_search_kernel<MODEL, KW, JTB_CTAS_EAGER, true>) | preload(ctx, wgl_tpc_kernel<MODEL, KW, true>) |
+                      preload(ctx, wgl_scout_kernel<MODEL, KW, true>))
+                   : (preload(ctx, wgl_search_kernel<MODEL, KW, JTB_CTAS_EXACT, false>) | preload(ctx, wgl_tpc_kernel<MODEL, KW, false>) |
+                      preload(ctx, wgl_scout_kernel<MODEL, KW, false>));
     rc |= preload(ctx, table_rehash_kernel<KW>) | preload(ctx, ring_compact_kernel<EW>) | preload(ctx, wgl_resume_ctrl_kernel);
     return rc ? -1 : 0;
 }
@@ -305,17 +335,25 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         if (ensure(ctx, ctx->ctrl, sizeof(Ctrl)) || ensure(ctx, ctx->found, n_shards * sizeof(int)) ||
             ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
             return -1;
-        // CTA deque / grid
+        // CTA deque / grid.  Two interchangeable search kernels: "tpc" (one THREAD per configuration, jtb_search.cuh:
+        // throughput) and "warp" (one WARP per configuration, jtb_wgl.cuh: every child of a configuration probed in
+        // the same round trip).  Default tpc; env JTB_KERNEL=warp|tpc overrides (A/B measurements).
+        const bool eager_mode = !(ctx->opts.flags & JTB_OPT_NO_EAGER_READS);
+        bool use_tpc = true;
+        if (const char* kk = getenv("JTB_KERNEL")) use_tpc = std::strcmp(kk, "warp") != 0;
         const int cand_rounds = P.S_pad / 32, cls_rounds = (P.max_nc + 31) / 32;
-        const uint32_t worst_push = WGL_BATCH * 32 * (cand_rounds + cls_rounds);   // per CTA step (overflow -> ring)
+        // worst case of children one CTA step can push (overflow -> ring)
+        const uint32_t worst_push = use_tpc ? (uint32_t)TPC_THREADS * (uint32_t)std::min(P.S_pad + P.max_nc, 64)
+                                            : (WGL_BATCH + WGL_WARPS) * 32 * (cand_rounds + cls_rounds);
         uint32_t deque_cap = 1024;                       // fixed: a full deque overflows to the ring
         while ((size_t)deque_cap * EW * 8 > 48 * 1024) deque_cap >>= 1;
         const uint32_t stage_cap = std::max(deque_cap, worst_push);
-        const size_t smem = (size_t)(deque_cap + WGL_BATCH) * EW * 8;   // deque + staged batch
-        // eager-read searches are small and latency-bound: 3 CTAs/SM (no register spills) wins; the
+        const size_t smem = use_tpc ? (size_t)deque_cap * EW * 8 : (size_t)(deque_cap + WGL_BATCH) * EW * 8;
+        // warp kernel: eager-read searches are small and latency-bound: 3 CTAs/SM (no register spills) wins; the
         // Knossos-exact space is throughput-bound: 4 CTAs/SM (measured A/B)
-        const int want_ctas = (ctx->opts.flags & JTB_OPT_NO_EAGER_READS) ? JTB_CTAS_EXACT : JTB_CTAS_EAGER;
+        const int want_ctas = use_tpc ? JTB_TPC_CTAS : (eager_mode ? JTB_CTAS_EAGER : JTB_CTAS_EXACT);
         int ctas_per_sm = (int)std::min<size_t>(want_ctas, (220 * 1024) / (smem + 1024));
+        if (getenv("JTB_CTAS_PER_SM")) ctas_per_sm = std::min(ctas_per_sm, std::max(1, atoi(getenv("JTB_CTAS_PER_SM"))));
         ctas_per_sm = std::max(1, ctas_per_sm);
         const int grid = ctx->opts.search_ctas ? (int)ctx->opts.search_ctas : ctx->n_sms * ctas_per_sm;
         const uint64_t per_step_push = (uint64_t)grid * stage_cap;  // worst case children of one step of every CTA
@@ -380,6 +418,19 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             return 0;
         };
         int attempts = 0;
+        // table placement: plain hash, or (experiment switch JTB_WIN_LOG2) rank-windowed: a window of 2^JTB_WIN_LOG2
+        // slots whose origin moves by ~n_slots / n_ranks slots per frontier rank, so that the whole table is used
+        auto geometry = [&](uint64_t slots, uint64_t& win_mask, uint64_t& rank_stride) {
+            win_mask = slots - 1;
+            rank_stride = 0;
+            if (const char* wl = getenv("JTB_WIN_LOG2")) {
+                const int lg = atoi(wl);
+                if (lg > 0 && (1ull << lg) < slots) {
+                    win_mask = (1ull << lg) - 1;
+                    rank_stride = std::max<uint64_t>(1, (slots - (1ull << lg)) / (uint64_t)std::max<int64_t>(1, P.n_ranks));
+                }
+            }
+        };
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         WglParams pb{};   // what the search kernel and the scouts share
         pb.rows = (const int32_t*)ctx->rows.p;
@@ -439,6 +490,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             WglParams p = pb;
             p.table = (uint64_t*)ctx->table.p;
             p.slot_mask = n_slots - 1;
+            geometry(n_slots, p.win_mask, p.rank_stride);
             p.ring = (uint64_t*)ctx->pool.p;
             p.ring_mask = ring_entries - 1;
             p.ring_guard = (tiny_ring && attempts == 1) ? 20000 : ring_entries - 3 * per_step_push;
@@ -453,7 +505,11 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             p.deque_cap = deque_cap;
             p.cas_first = getenv("JTB_CAS_FIRST") ? atoi(getenv("JTB_CAS_FIRST")) : 0;
             int rc;
-            if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem, ctas_per_sm);
+            if (use_tpc) {
+                if (m->kind == JTB_MODEL_BANK) rc = launch_tpc_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem);
+                else if (m->kind == JTB_MODEL_SET) rc = launch_tpc<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem);
+                else rc = launch_tpc_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, grid, smem);
+            } else if (m->kind == JTB_MODEL_BANK) rc = launch_wgl_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, grid, smem, ctas_per_sm);
             else if (m->kind == JTB_MODEL_SET) rc = launch_wgl<JTB_MODEL_SET, 2>(ctx, p, 0, grid, smem, ctas_per_sm);
             else rc = launch_wgl_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, grid, smem, ctas_per_sm);
             if (rc) { free_tmp(); return rc; }
@@ -484,9 +540,11 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
                 const uint64_t new_slots = n_slots * 4;
                 if (grow_buf(table2, new_slots * KW * 8)) { free_tmp(); return -1; }
                 CK(cudaMemsetAsync(table2.p, 0, new_slots * KW * 8, ctx->stream));
-                if (KW == 2) table_rehash_kernel<2><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
-                else if (KW == 4) table_rehash_kernel<4><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
-                else table_rehash_kernel<8><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1);
+                uint64_t g_win, g_stride;
+                geometry(new_slots, g_win, g_stride);
+                if (KW == 2) table_rehash_kernel<2><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride);
+                else if (KW == 4) table_rehash_kernel<4><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride);
+                else table_rehash_kernel<8><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride);
                 CK(cudaGetLastError());
                 CK(cudaStreamSynchronize(ctx->stream));
                 std::swap(ctx->table, table2);
@@ -535,6 +593,11 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             st[15] = sc_ctl[2]; st[16] = sc_ctl[3]; st[17] = sc_ctl[4]; st[18] = (unsigned long long)n_scouts;
         }
         if (hc.stop == 2 && hc.cause == CAUSE_RING_FULL) hc.cause = JTB_CAUSE_BUDGET;
+        if (hc.overflow) {   // a ring slot was overwritten before it was consumed: no verdict may be derived from this search
+            hc.stop = 2;
+            hc.cause = JTB_CAUSE_BUDGET;
+            std::fill(h_found.begin(), h_found.end(), 0);
+        }
         for (int s : searchable) {
             jtb_lin_shard& r = shards[s];
             if (h_found[s]) {
@@ -744,6 +807,19 @@ int jtb_table_bench(jtb_ctx* ctx, uint64_t n_keys, int variant, int rounds, doub
     if (ensure(ctx, ctx->table, n_slots * 16)) return -1;
     return run_table_bench(ctx->stream, ctx->ev0, ctx->ev1, (uint64_t*)ctx->table.p, n_slots, n_keys, variant, rounds,
                            ctx->n_sms, insert_seconds, probe_seconds, found, ctx->err);
+}
+
+int jtb_gather_bench(jtb_ctx* ctx, uint64_t table_bytes, int in_flight, int wide, uint32_t iters, int ctas_per_sm,
+                     int rounds, double* seconds, uint64_t* n_probes) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    ctx->fc.valid = false;
+    uint64_t n_slots = 1;
+    while (n_slots * 2 * 16 <= table_bytes) n_slots <<= 1;
+    if (ensure(ctx, ctx->table, n_slots * 16)) return -1;
+    return run_gather_bench(ctx->stream, ctx->ev0, ctx->ev1, (uint64_t*)ctx->table.p, n_slots, in_flight, wide, iters,
+                            std::max(1, ctas_per_sm), std::max(1, rounds), ctx->n_sms, seconds, n_probes, ctx->err);
 }
 
 }  // extern "C"

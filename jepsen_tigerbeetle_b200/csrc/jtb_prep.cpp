@@ -70,8 +70,14 @@ OpRec resolve(const jtb_history* h, const jtb_model* m, int64_t ev, Prepared& ou
                 bal[sl] = pl[i + 1];
             }
             r.y = care;
-            r.z = (int32_t)(out.read_bal.size() / JTB_MAX_ACCOUNTS);
+            r.w = (int32_t)(out.read_bal.size() / JTB_MAX_ACCOUNTS);   // host-side index; replaced by the invocation position
             out.read_bal.insert(out.read_bal.end(), bal, bal + JTB_MAX_ACCOUNTS);
+            if (care == (1 << m->n_accounts) - 1 && !(r.x & OP_IMPOSSIBLE)) {
+                uint32_t hsh = 0;
+                for (int i = 0; i < JTB_MAX_ACCOUNTS; ++i) hsh += (uint32_t)bal[i] * bank_hash_c(i);
+                r.x |= OP_HASHED;
+                r.z = (int32_t)hsh;
+            }
         } else {
             r.x |= OP_IMPOSSIBLE;
         }
@@ -385,6 +391,7 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
         // op records (completed ops only live in the table; crashed ones live in class records)
         std::vector<int32_t> gid(t.ops.size(), -1);
         std::vector<int32_t> op_inv_pos;   // by gid - op_base
+        std::vector<int32_t> op_read_bal;  // by gid - op_base: bank reads' row in read_bal (resolve() left it in .w)
         for (int i = 0; i < (int)t.ops.size(); ++i) {
             if (t.ops[i].crashed) continue;
             gid[i] = (int32_t)out.ops.size();
@@ -394,6 +401,7 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
             // depth-first scouts order their candidates by it.  Bank transfers need .w for the credit slot:
             // theirs goes into the first (otherwise unused) payload word of the row cell.
             op_inv_pos.push_back(t.ops[i].inv_pos);
+            op_read_bal.push_back(out.ops.back().w);
             const bool transfer = m->kind == JTB_MODEL_BANK && (out.ops.back().x & 0xff) == JTB_F_TRANSFER;
             if (!transfer) out.ops.back().w = t.ops[i].inv_pos;
         }
@@ -435,7 +443,8 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
                 cell[0] = rec.x; cell[1] = rec.y; cell[2] = rec.z; cell[3] = rec.w;
                 if (m->kind == JTB_MODEL_BANK) {
                     if ((rec.x & 0xff) == JTB_F_READ)
-                        std::memcpy(cell + 4, &out.read_bal[(size_t)rec.z * JTB_MAX_ACCOUNTS], 8 * sizeof(int32_t));
+                        std::memcpy(cell + 4, &out.read_bal[(size_t)op_read_bal[cur[sl] - op_base] * JTB_MAX_ACCOUNTS],
+                                    8 * sizeof(int32_t));
                     else
                         cell[4] = op_inv_pos[cur[sl] - op_base];
                 }
@@ -450,6 +459,19 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
                 // not expressible: the shard is reported UNKNOWN (too wide); neutralise its rows
                 out.shard_cause[s] = JTB_CAUSE_TOO_WIDE;
             }
+        }
+        // slot masks of every row (after the set model has marked its impossible reads)
+        for (int j = 0; j < R; ++j) {
+            int32_t* row = &out.rows[(size_t)(base + j) * RW];
+            uint64_t occ = 0, rd = 0;
+            for (int sl = 0; sl < out.S_pad; ++sl) {
+                const int32_t x = row[ROW_EXTRA + sl * SW];
+                if (x < 0 || (x & OP_IMPOSSIBLE)) continue;
+                occ |= 1ull << sl;
+                if ((x & 0xff) == JTB_F_READ) rd |= 1ull << sl;
+            }
+            std::memcpy(row + 14, &occ, 8);
+            std::memcpy(row + 16, &rd, 8);
         }
     }
     return true;

@@ -25,6 +25,16 @@ struct OpRec {
     int32_t x, y, z, w;
 };
 constexpr int OP_IMPOSSIBLE = 1 << 8;
+// bank reads that cover every account: OpRec.z holds bank_hash() of the expected balances, so a candidate read is
+// rejected with one 32-bit compare (the hash is linear in the balances: equal balances => equal hash)
+constexpr int OP_HASHED = 1 << 9;
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr uint32_t bank_hash_c(int i) {
+    return i == 0 ? 0x9E3779B1u : i == 1 ? 0x85EBCA77u : i == 2 ? 0xC2B2AE3Du : i == 3 ? 0x27D4EB2Fu :
+           i == 4 ? 0x165667B1u : i == 5 ? 0xD3A2646Du : i == 6 ? 0xFD7046C5u : 0xB55A4F09u;
+}
 
 // Crashed-op equivalence class (same f and value): members are linearized in invocation order only,
 // so a config records just how many of the class it has consumed (a count field inside the key).
@@ -45,14 +55,16 @@ struct ClassRec {
 //   [11]       first class record of the shard
 //   [12]       number of classes of the shard
 //   [13]       slot of this rank's own op
-//   [14..15]   pad
-//   [16 + t*SW, 16 + (t+1)*SW)   the op occupying open-op slot t at that return event, INLINE:
+//   [14..15]   u64 mask of the slots that hold a linearizable op at this return (empty / impossible ops excluded)
+//   [16..17]   u64 mask of those slots whose op is a READ (never changes the model state)
+//   [18..19]   pad
+//   [20 + t*SW, 20 + (t+1)*SW)   the op occupying open-op slot t at that return event, INLINE:
 //        words 0..3  OpRec (x = -1: slot empty)
 //        bank  (SW = 12): words 4..11 = the 8 balances a read expects (by account slot; op.y = care mask);
 //                         word 4 of a TRANSFER = its invocation position
 //        set   (SW = 8):  words 4..7  = (need, care) u64 pair of a read AT THIS RANK:
 //                         consistent <=> (key word1 & care) == need
-constexpr int ROW_EXTRA = 16;
+constexpr int ROW_EXTRA = 20;
 inline int slot_words(int model) { return model == JTB_MODEL_BANK ? 12 : model == JTB_MODEL_SET ? 8 : 4; }
 constexpr int OP_EMPTY = -1;
 

@@ -604,6 +604,12 @@ inline int run_bank_totals(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, cons
         out->lowest_index = agg.lowest_idx; out->highest_index = agg.highest_idx;
     }
     out->valid = out->error_count ? JTB_INVALID : JTB_VALID;
+    // reference quirk (tests/ledger.clj:122-123 with the default :total-amount 0, :356): err-badness divides by zero as
+    // soon as util/max-by has two :wrong-total errors to compare -> the checker throws -> check-safe: :unknown
+    if (total_amount == 0 && agg.count[JTB_BANK_WRONG_TOTAL] >= 2) {
+        out->reference_throws = 1;
+        out->valid = JTB_UNKNOWN;
+    }
     cleanup();
     out->seconds_kernel = ms * 1e-3;
     out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_start;

@@ -11,6 +11,7 @@
 //                       mbarrier; buckets are then scanned in shared memory
 // Variants 1 and 2 use a bucketed layout (home bucket = hash, slot = first empty in the bucket).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <string>
 
@@ -198,6 +199,74 @@ __global__ void __launch_bounds__(128) tb_probe_buckets_tma(const uint64_t* tabl
     }
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     if (lane == 0) atomicAdd(found, mine);
+}
+
+// ---- random-gather sweep: what the memory system gives a hash probe, as a function of the table's footprint ----------
+// Every thread walks its own pseudo-random slot sequence (xorshift32 + one multiply: the address generation costs a
+// handful of instructions, so the ALUs are not what is measured) with U independent 16 B loads (ld.global.cg.v2.u64,
+// exactly the search kernel's probe) in flight; WIDE = 2 also loads the other half of the 32 B sector.  The loaded
+// words are folded into a checksum so nothing is optimised away.  Footprints from 64 MiB (L2-resident: 126 MB L2) to
+// 16 GiB show where random 16 B probes stop being served by L2 and what DRAM / the TLBs sustain beyond it.
+template <int U, int WIDE>
+__global__ void __launch_bounds__(256) tb_gather(const uint64_t* __restrict__ table, uint64_t slot_mask, uint32_t iters,
+                                                 unsigned long long* sink) {
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint64_t acc = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        K128 v[U], w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+            const uint64_t idx = ((uint64_t)x * 0x9E3779B97F4A7C15ull >> 20) & slot_mask;
+            v[u] = ldcg128(table + idx * 2);
+            if (WIDE == 2) w[u] = ldcg128(table + (idx ^ 1) * 2);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            acc ^= v[u].lo + v[u].hi;
+            if (WIDE == 2) acc ^= w[u].lo + w[u].hi;
+        }
+    }
+    if (acc == 0x123456789abcdefull) atomicAdd(sink, 1ull);   // never true in practice: keeps the loads alive
+}
+
+template <int U, int WIDE>
+int launch_gather(cudaStream_t st, const uint64_t* table, uint64_t slot_mask, uint32_t iters, int grid,
+                  unsigned long long* sink) {
+    tb_gather<U, WIDE><<<grid, 256, 0, st>>>(table, slot_mask, iters, sink);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// loads = grid * 256 * iters * U probes of 16 B (x WIDE); returns seconds (CUDA events), best of `rounds`
+inline int run_gather_bench(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, uint64_t* table, uint64_t n_slots, int in_flight,
+                            int wide, uint32_t iters, int ctas_per_sm, int rounds, int n_sms, double* seconds,
+                            uint64_t* n_probes, std::string& err) {
+    unsigned long long* d_sink = nullptr;
+    if (cudaMalloc(&d_sink, 8) != cudaSuccess) { err = "cudaMalloc failed"; return -1; }
+    cudaMemsetAsync(d_sink, 0, 8, st);
+    // non-zero contents (an all-zero table could be served by compression / zero pages)
+    if (cudaMemsetAsync(table, 0x5a, n_slots * 16, st) != cudaSuccess) { err = "memset failed"; cudaFree(d_sink); return -1; }
+    const int grid = n_sms * ctas_per_sm;
+    double best = 1e30;
+    for (int r = 0; r < rounds + 1; ++r) {   // first round = warm-up
+        cudaEventRecord(e0, st);
+        int rc = -1;
+        const uint64_t mask = n_slots - 1;
+#define JTB_G(U_, W_) rc = launch_gather<U_, W_>(st, table, mask, iters, grid, d_sink)
+        if (wide == 2) { if (in_flight <= 2) JTB_G(2, 2); else if (in_flight <= 4) JTB_G(4, 2); else if (in_flight <= 8) JTB_G(8, 2); else JTB_G(16, 2); }
+        else { if (in_flight <= 1) JTB_G(1, 1); else if (in_flight <= 2) JTB_G(2, 1); else if (in_flight <= 4) JTB_G(4, 1); else if (in_flight <= 8) JTB_G(8, 1); else JTB_G(16, 1); }
+#undef JTB_G
+        cudaEventRecord(e1, st);
+        if (rc || cudaStreamSynchronize(st) != cudaSuccess) { err = "gather kernel failed"; cudaFree(d_sink); return -1; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0) best = std::min(best, (double)ms * 1e-3);
+    }
+    cudaFree(d_sink);
+    const int u = in_flight <= 1 ? 1 : in_flight <= 2 ? 2 : in_flight <= 4 ? 4 : in_flight <= 8 ? 8 : 16;
+    *seconds = best;
+    *n_probes = (uint64_t)grid * 256ull * iters * (uint64_t)(wide == 2 && u < 2 ? 2 : u);
+    return 0;
 }
 
 inline int run_table_bench(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, uint64_t* table, uint64_t n_slots,

@@ -48,6 +48,7 @@ struct Ctrl {
     alignas(128) int stop;         // 0 run, 1 finished (all shards decided or exhausted), 2 paused/aborted (cause)
     int cause;                     // JTB_CAUSE_* / CAUSE_RING_FULL when stop == 2
     int n_undecided;               // shards not yet found VALID
+    int overflow;                  // a ring slot was overwritten before it was consumed: the verdict is void (UNKNOWN)
     alignas(128) unsigned long long head;   // read tickets handed to warps (ring positions)
     alignas(128) unsigned long long tail;   // entries pushed (ring positions reserved for writing)
     alignas(128) unsigned long long created;   // configs created (initial + every new child)
@@ -64,6 +65,8 @@ struct WglParams {
     const int32_t* cls_inv_pos;
     uint64_t* table;        // slots of KW 64-bit words
     uint64_t slot_mask;     // n_slots - 1
+    uint64_t win_mask;      // rank-windowed placement: home slot = (rank * rank_stride + (hash & win_mask)) & slot_mask;
+    uint64_t rank_stride;   //   win_mask == slot_mask, rank_stride == 0 is the plain hash table
     uint64_t* ring;         // work queue: entries of EW words, word0 != 0 <=> slot holds an entry
     uint64_t ring_mask;     // ring entries - 1
     uint64_t ring_guard;    // pause when (tail - head) exceeds this
@@ -142,10 +145,19 @@ __device__ __forceinline__ uint64_t hash_key(const uint64_t (&k)[KW]) {
 
 // Visited-table probe + insert.  Returns 1 = inserted (new config), 0 = already present,
 // -1 = table exhausted.  *plen gets the number of slots inspected.
+// Home slot of a key.  Plain table: hash & slot_mask.  Rank-windowed table (win_mask < slot_mask): the hash only picks
+// a position inside a window of win_mask + 1 slots whose origin moves with the key's frontier rank, so the probes of
+// a search that works on a narrow band of ranks stay inside a few windows (L2-resident) instead of all of HBM.
 template <int KW>
-__device__ __forceinline__ int table_insert(uint64_t* table, uint64_t slot_mask, const uint64_t (&k)[KW],
-                                            int* plen, bool cas_first = false) {
-    uint64_t idx = hash_key<KW>(k) & slot_mask;
+__device__ __forceinline__ uint64_t table_home(const uint64_t (&k)[KW], uint64_t slot_mask, uint64_t win_mask,
+                                               uint64_t rank_stride) {
+    const uint64_t rank = (k[0] >> 32) & RANK_MASK;
+    return (rank * rank_stride + (hash_key<KW>(k) & win_mask)) & slot_mask;
+}
+
+template <int KW>
+__device__ __forceinline__ int table_insert_at(uint64_t* table, uint64_t slot_mask, uint64_t idx,
+                                               const uint64_t (&k)[KW], int* plen, bool cas_first = false) {
     for (int i = 0; i < MAX_PROBE; ++i) {
         uint64_t* slot = table + idx * KW;
         // load-first: hits (the majority) cost one plain load; cas-first: new configs cost one round trip
@@ -181,6 +193,18 @@ __device__ __forceinline__ int table_insert(uint64_t* table, uint64_t slot_mask,
     }
     *plen = MAX_PROBE;
     return -1;
+}
+
+template <int KW>
+__device__ __forceinline__ int table_insert(uint64_t* table, uint64_t slot_mask, const uint64_t (&k)[KW],
+                                            int* plen, bool cas_first = false) {
+    return table_insert_at<KW>(table, slot_mask, hash_key<KW>(k) & slot_mask, k, plen, cas_first);
+}
+
+template <int KW>
+__device__ __forceinline__ int table_insert_p(const WglParams& p, const uint64_t (&k)[KW], int* plen, bool cas_first = false) {
+    return table_insert_at<KW>(p.table, p.slot_mask, table_home<KW>(k, p.slot_mask, p.win_mask, p.rank_stride), k, plen,
+                               cas_first);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -337,7 +361,7 @@ __device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, co
                 }
             } else {
                 int plen;
-                const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
+                const int res = table_insert_p<KW>(p, cw, &plen, cas_first);
                 my_probes++;
                 my_max_probe = max(my_max_probe, plen);
                 if (res < 0) {
@@ -392,7 +416,7 @@ __device__ __forceinline__ void expand_config(const WglParams& p, Ctrl* ctrl, co
         int is_new = 0;
         if (ok) {
             int plen;
-            const int res = table_insert<KW>(p.table, p.slot_mask, cw, &plen, cas_first);
+            const int res = table_insert_p<KW>(p, cw, &plen, cas_first);
             my_probes++;
             my_max_probe = max(my_max_probe, plen);
             if (res < 0) {
@@ -710,7 +734,7 @@ __global__ void __launch_bounds__(WGL_THREADS, MINB) wgl_search_kernel(const Wgl
                 int res = 0;
                 if (lane == 0) {
                     int plen;
-                    res = table_insert<KW>(p.table, p.slot_mask, w, &plen, cas_first);
+                    res = table_insert_p<KW>(p, w, &plen, cas_first);
                 }
                 res = __shfl_sync(0xffffffffu, res, 0);
                 if (res <= 0) {
@@ -784,14 +808,14 @@ __global__ void ring_compact_kernel(const uint64_t* __restrict__ old_ring, uint6
 // Re-inserts every key of a full table into a larger one (table growth without losing work).
 template <int KW>
 __global__ void table_rehash_kernel(const uint64_t* __restrict__ old_table, uint64_t old_slots, uint64_t* new_table,
-                                    uint64_t new_mask) {
+                                    uint64_t new_mask, uint64_t win_mask, uint64_t rank_stride) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_slots; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t k[KW];
 #pragma unroll
         for (int w = 0; w < KW; ++w) k[w] = old_table[i * KW + w];
         if (k[0] == 0) continue;
         int plen;
-        table_insert<KW>(new_table, new_mask, k, &plen);
+        table_insert_at<KW>(new_table, new_mask, table_home<KW>(k, new_mask, win_mask, rank_stride), k, &plen);
     }
 }
 

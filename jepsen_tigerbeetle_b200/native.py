@@ -16,15 +16,17 @@ from .history import CModel, FlatHistory, as_c_history
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JTB_LIB_PATH") or os.path.join(_HERE, "libjtb_check.so")  # env: A/B experiments only
 CSRC = os.path.join(_HERE, "csrc")
-_SOURCES = ["jtb_abi.cu", "jtb_prep.cpp"]
-_DEPS = _SOURCES + ["jtb_prep.h", "jtb_wgl.cuh", "jtb_scout.cuh", "jtb_scans.cuh", "jtb_table_bench.cuh"]
+_SOURCES = ["jtb_abi.cu", "jtb_prep.cpp", "jtb_multi.cpp"]
+_DEPS = _SOURCES + ["jtb_prep.h", "jtb_expand.h", "jtb_wgl.cuh", "jtb_search.cuh", "jtb_scout.cuh", "jtb_scans.cuh",
+                    "jtb_table_bench.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
            "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds", "jtb_prepare_info",
-           "jtb_final_configs"]
+           "jtb_final_configs", "jtb_gather_bench", "jtb_multi_create", "jtb_multi_create_error", "jtb_multi_destroy", "jtb_multi_n_gpus",
+           "jtb_multi_last_error", "jtb_multi_check_linearizable", "jtb_multi_check_set_full"]
 
 _lib = None
 _lock = threading.Lock()
@@ -72,6 +74,17 @@ def lib() -> C.CDLL:
             L.jtb_check_bank_totals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
             L.jtb_table_bench.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
+            L.jtb_gather_bench.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p]
+            L.jtb_multi_create.restype = C.c_void_p
+            L.jtb_multi_create.argtypes = [C.c_void_p, C.c_int]
+            L.jtb_multi_create_error.restype = C.c_char_p
+            L.jtb_multi_destroy.argtypes = [C.c_void_p]
+            L.jtb_multi_n_gpus.argtypes = [C.c_void_p]
+            L.jtb_multi_last_error.restype = C.c_char_p
+            L.jtb_multi_last_error.argtypes = [C.c_void_p]
+            L.jtb_multi_check_linearizable.argtypes = [C.c_void_p] * 6
+            L.jtb_multi_check_set_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
             if L.jtb_abi_version() != abi.ABI_VERSION:
                 raise NativeError("ABI version mismatch between libjtb_check.so and abi.py")
             _lib = L
@@ -145,7 +158,8 @@ class Context:
         if rc != 0:
             raise NativeError(f"jtb_check_bank_totals rc={rc}: {self._err()}")
         return {
-            "valid": res.valid, "read_count": res.read_count, "error_count": res.error_count,
+            "valid": res.valid, "reference_throws": res.reference_throws, "read_count": res.read_count,
+            "error_count": res.error_count,
             "first_error_index": res.first_error_index, "first_error_type": res.first_error_type,
             "count_by_type": list(res.count_by_type),
             "first_index_by_type": list(res.first_index_by_type),
@@ -186,6 +200,81 @@ class Context:
             raise NativeError(f"jtb_table_bench rc={rc}: {self._err()}")
         return {"insert_seconds": ins.value, "probe_seconds": prb.value, "found": found.value,
                 "n_keys": n_keys, "rounds": rounds, "variant": variant}
+
+
+class MultiContext:
+    """`jtb_multi`: the in-library multi-GPU fan-out (one process, n_gpus devices, one NCCL all-reduce(MAX) of the
+    per-shard verdict vector) — what a single-process JVM host binds instead of `independent/checker`'s thread pool."""
+
+    def __init__(self, n_gpus: int = 0, table_bytes: int = 0, max_configs: int = 0, time_budget_ms: int = 0,
+                 eager_reads: bool = True, scouts: bool = True) -> None:
+        L = lib()
+        flags = (0 if eager_reads else abi.OPT_NO_EAGER_READS) | (0 if scouts else abi.OPT_NO_SCOUTS)
+        opts = abi.COpts(0, flags, table_bytes, max_configs, time_budget_ms, 0)
+        self._h = L.jtb_multi_create(C.byref(opts), n_gpus)
+        if not self._h:
+            raise NativeError(f"jtb_multi_create failed: {L.jtb_multi_create_error().decode()}")
+        self.n_gpus = L.jtb_multi_n_gpus(self._h)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().jtb_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def check_linearizable(self, h: FlatHistory, model: CModel) -> dict:
+        ch = as_c_history(h)
+        shards = (abi.CLinShard * h.n_shards)()
+        res = abi.CLinResult()
+        dev = (C.c_int32 * max(1, h.n_shards))()
+        rc = lib().jtb_multi_check_linearizable(self._h, C.addressof(ch), C.addressof(model), C.addressof(shards),
+                                                C.addressof(res), C.addressof(dev))
+        if rc != 0:
+            raise NativeError(f"jtb_multi_check_linearizable rc={rc}: {lib().jtb_multi_last_error(self._h).decode()}")
+        return {
+            "valid": res.valid, "n_failures": res.n_failures, "configs": res.configs_explored, "probes": res.probes,
+            "hbm_bytes_algorithmic": res.hbm_bytes_algorithmic, "key_bytes": res.key_bytes,
+            "seconds_kernel": res.seconds_kernel, "seconds_total": res.seconds_total,
+            "device_of_shard": [dev[s] for s in range(h.n_shards)],
+            "shards": [{"valid": s.valid, "witness_index": s.witness_index, "previous_ok_index": s.previous_ok_index,
+                        "cause": s.cause, "configs": s.configs_explored, "probes": s.probes} for s in shards],
+        }
+
+    def check_set_full(self, h: FlatHistory, linearizable: bool = True) -> dict:
+        ch = as_c_history(h)
+        shards = (abi.CSetFullShard * h.n_shards)()
+        out = abi.CSetFullOut()
+        out.shards = C.cast(shards, C.c_void_p)
+        dev = (C.c_int32 * max(1, h.n_shards))()
+        rc = lib().jtb_multi_check_set_full(self._h, C.addressof(ch), int(linearizable), C.addressof(out),
+                                            C.addressof(dev))
+        if rc != 0:
+            raise NativeError(f"jtb_multi_check_set_full rc={rc}: {lib().jtb_multi_last_error(self._h).decode()}")
+        fields = [f for f, _ in abi.CSetFullShard._fields_]
+        return {"valid": out.valid, "n_failures": out.n_failures, "raia_valid": out.raia_valid,
+                "n_suspect": out.n_suspect, "seconds_kernel": out.seconds_kernel, "seconds_total": out.seconds_total,
+                "device_of_shard": [dev[s] for s in range(h.n_shards)],
+                "shards": [{f: getattr(s, f) for f in fields} for s in shards]}
+
+
+def gather_bench(ctx: "Context", table_bytes: int, in_flight: int = 4, wide: int = 1, iters: int = 64,
+                 ctas_per_sm: int = 8, rounds: int = 3) -> dict:
+    """Random 16 B gathers over a table of `table_bytes` (see `jtb_gather_bench`)."""
+    sec, n = C.c_double(), C.c_uint64()
+    rc = lib().jtb_gather_bench(ctx._h, table_bytes, in_flight, wide, iters, ctas_per_sm, rounds, C.addressof(sec),
+                                C.addressof(n))
+    if rc != 0:
+        raise NativeError(f"jtb_gather_bench rc={rc}: {ctx._err()}")
+    return {"table_bytes": table_bytes, "in_flight": in_flight, "wide": wide, "ctas_per_sm": ctas_per_sm,
+            "probes": n.value, "seconds": sec.value, "Gprobes_s": n.value / sec.value / 1e9,
+            "algo_GBps": 16 * wide * n.value / sec.value / 1e9}
 
 
 def prepare_seconds(h: FlatHistory, model: CModel) -> float:

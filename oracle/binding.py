@@ -13,14 +13,39 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+def _cpu_stamp() -> str:
+    """Identity of the host CPU: the oracle is compiled -march=native, so a library built on another machine
+    (it travels to the GPU box with the snapshot) must be rebuilt there."""
+    try:
+        model, flags = "", ""
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+            if model and flags:
+                break
+        import hashlib
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:12]
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libjtb_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("lin_oracle.cpp", "scan_oracle.cpp", "oracle_common.h")]
+    stamp_file = os.path.join(_HERE, ".build_cpu")
+    srcs = [os.path.join(_HERE, f) for f in ("lin_oracle.cpp", "scan_oracle.cpp", "oracle_common.h", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "jtb_check.h"))
     stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
-    if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"],
-                              stdout=subprocess.DEVNULL)
+    stamp = _cpu_stamp()
+    try:
+        other_cpu = open(stamp_file).read() != stamp
+    except OSError:
+        other_cpu = True
+    if force or stale or other_cpu:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "-s"], stdout=subprocess.DEVNULL)
+        with open(stamp_file, "w") as f:
+            f.write(stamp)
     return so
 
 
@@ -86,7 +111,8 @@ def check_bank_totals(h: FlatHistory, model: CModel, total_amount: int = 0) -> d
 
 def bank_to_dict(res) -> dict:
     return {
-        "valid": res.valid, "read_count": res.read_count, "error_count": res.error_count,
+        "valid": res.valid, "reference_throws": res.reference_throws, "read_count": res.read_count,
+        "error_count": res.error_count,
         "first_error_index": res.first_error_index, "first_error_type": res.first_error_type,
         "count_by_type": list(res.count_by_type),
         "first_index_by_type": list(res.first_index_by_type),

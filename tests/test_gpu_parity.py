@@ -176,6 +176,25 @@ def test_bank_totals(gpu_ctx, oracle_mod):
                 assert g[k] == o[k], (k, neg_ok)
 
 
+def test_bank_totals_total_amount_zero_quirk(gpu_ctx, oracle_mod):
+    """tests/ledger.clj:122-123 with :total-amount 0: two :wrong-total reads make the reference throw -> :unknown."""
+    from jepsen_tigerbeetle_b200 import checker as ck
+    z = "3 0 4 0 5 0 6 0 7 0 8 0"
+    one = f"0:inv read, 0:ok read {{1 1 2 0 {z}}}"
+    two = one + f", 0:inv read, 0:ok read {{1 -7 2 0 {z}}}"
+    m = model_for("bank")
+    for text, total, expect in ((one, 0, (H.INVALID, 0)), (two, 0, (H.UNKNOWN, 1)), (two, 10, (H.INVALID, 0))):
+        h = H.flatten_ops(kat.ops(text), "bank")
+        g, o = gpu_ctx.check_bank_totals(h, m, total), oracle_mod.check_bank_totals(h, m, total)
+        assert (g["valid"], g["reference_throws"]) == expect
+        for k in g:
+            if not k.startswith("seconds"):
+                assert g[k] == o[k], k
+    r = ck.bank_checker({"negative-balances?": True}, ctx=gpu_ctx).check(
+        {"accounts": list(range(1, 9)), "total-amount": 0}, kat.ops(two))
+    assert r["valid?"] == "unknown" and "Divide by zero" in r["error"] and r["error-count"] == 2
+
+
 def test_read_all_invoked_adds(gpu_ctx, oracle_mod):
     """workloads/set_full.clj:51-75 on the device: final reads that miss invoked adds."""
     h = synth.config_c4(seed=3, n_keys=4, n_ops=4000)

@@ -157,3 +157,25 @@ def test_bank_totals_kats(oracle_mod):
     assert (r["lowest_total"], r["lowest_index"], r["highest_total"], r["highest_index"]) == (-7, 3, 4, 7)
     assert r["worst_index_by_type"][3] == 3 and r["first_error_index"] == 1
     del m
+
+
+def test_bank_totals_total_amount_zero_quirk(oracle_mod):
+    """tests/ledger.clj:122-123: err-badness computes (/ (- total total-amount) total-amount); with the default
+    :total-amount 0 (tests/ledger.clj:356) that is an integer division by zero.  util/max-by only calls it when an
+    error type has >= 2 members, so ONE :wrong-total read gives {:valid? false} but TWO make the reference checker
+    throw, which jepsen's check-safe reports as {:valid? :unknown}.  Oracle and device reproduce exactly that."""
+    z = "3 0 4 0 5 0 6 0 7 0 8 0"
+    def run(text, total=0):
+        return oracle_mod.check_bank_totals(H.flatten_ops(kat.ops(text), "bank"), model_for("bank"), total)
+    one = f"0:inv read, 0:ok read {{1 1 2 0 {z}}}"
+    two = one + f", 0:inv read, 0:ok read {{1 -7 2 0 {z}}}"
+    r = run(one)
+    assert (r["valid"], r["reference_throws"], r["error_count"]) == (H.INVALID, 0, 1)
+    r = run(two)
+    assert (r["valid"], r["reference_throws"], r["error_count"]) == (H.UNKNOWN, 1, 2)
+    assert r["count_by_type"][3] == 2 and r["worst_index_by_type"][3] == 3     # statistics are still filled
+    r = run(two, total=10)                                                      # a non-zero total: no division by zero
+    assert (r["valid"], r["reference_throws"]) == (H.INVALID, 0)
+    # other error types never divide: two :nil-balance reads stay {:valid? false}
+    r = run(f"0:inv read, 0:ok read {{1 nil 2 0 {z}}}, 0:inv read, 0:ok read {{1 nil 2 nil {z}}}")
+    assert (r["valid"], r["reference_throws"], r["count_by_type"][2]) == (H.INVALID, 0, 2)
