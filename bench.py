@@ -64,22 +64,8 @@ def config_block(args, n_gpus):
 
 def sharded_workloads(args):
     """BASELINE configs #5 and #4 with ONE poisoned key each (the merged verdict must flip)."""
-    import copy
-    c5 = copy.deepcopy(synth.config_c5(seed=1, n_ops=args.c5_ops))
-    # poison one key of C5: its third :ok read returns a value nobody ever wrote (values are 0..4)
-    s = 7
-    lo, hi = int(c5.shard_off[s]), int(c5.shard_off[s + 1])
-    reads = [e for e in range(lo, hi) if c5.f[e] == H.F_READ and c5.type[e] == H.T_OK]
-    c5.a[reads[min(2, len(reads) - 1)]] = 99
-    c4 = synth.config_c4(seed=1, n_keys=64, n_ops=args.c4_ops)
-    # poison one ledger of C4: an element that a read has seen disappears from the ledger's LAST ok read -> lost
-    c4 = copy.deepcopy(c4)
-    s = 5
-    lo, hi = int(c4.shard_off[s]), int(c4.shard_off[s + 1])
-    reads = [e for e in range(lo, hi) if c4.f[e] == H.F_READ and c4.type[e] == H.T_OK and c4.payload_len[e] > 4
-             and not (c4.flags[e] & 1)]
-    e = reads[-1]
-    c4.payload_len[e] -= 2          # payloads are sorted: the two largest (latest) ids vanish from this read ...
+    c5 = synth.poison_c5(synth.config_c5(seed=1, n_ops=args.c5_ops), 7)
+    c4 = synth.poison_c4(synth.config_c4(seed=1, n_keys=64, n_ops=args.c4_ops), 5)
     return c5, c4
 
 

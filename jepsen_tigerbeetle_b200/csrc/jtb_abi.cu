@@ -339,7 +339,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
         // throughput) and "warp" (one WARP per configuration, jtb_wgl.cuh: every child of a configuration probed in
         // the same round trip).  Default tpc; env JTB_KERNEL=warp|tpc overrides (A/B measurements).
         const bool eager_mode = !(ctx->opts.flags & JTB_OPT_NO_EAGER_READS);
-        bool use_tpc = true;
+        bool use_tpc = false;
         if (const char* kk = getenv("JTB_KERNEL")) use_tpc = std::strcmp(kk, "warp") != 0;
         const int cand_rounds = P.S_pad / 32, cls_rounds = (P.max_nc + 31) / 32;
         // worst case of children one CTA step can push (overflow -> ring)

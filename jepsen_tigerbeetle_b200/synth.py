@@ -318,3 +318,28 @@ def config_c5(seed: int = 1, n_keys: int = 256, p_info: float = 0.30, n_ops: int
     """50k-op adversarial cas-register history, 30% :info, 8 clients per key."""
     return generate(SynthSpec("cas-register", n_ops, 8 * n_keys, seed, p_info=p_info,
                               n_keys=n_keys, grouped_keys=True, **kw))
+
+
+def poison_c5(h: FlatHistory, shard: int = 7) -> FlatHistory:
+    """One key of a C5 history made non-linearizable: its third :ok read returns a value nobody ever wrote
+    (values are 0..4).  The merged verdict of the keyed check must flip to invalid with exactly one failure."""
+    import copy
+    from . import history as H
+    h = copy.deepcopy(h)
+    lo, hi = int(h.shard_off[shard]), int(h.shard_off[shard + 1])
+    reads = [e for e in range(lo, hi) if h.f[e] == H.F_READ and h.type[e] == H.T_OK]
+    h.a[reads[min(2, len(reads) - 1)]] = 99
+    return h
+
+
+def poison_c4(h: FlatHistory, shard: int = 5) -> FlatHistory:
+    """One ledger of a C4 history loses elements: the two largest ids vanish from the ledger's LAST non-final :ok read
+    (payloads are sorted), so elements a read has already seen are :lost -> set-full invalid for that ledger."""
+    import copy
+    from . import history as H
+    h = copy.deepcopy(h)
+    lo, hi = int(h.shard_off[shard]), int(h.shard_off[shard + 1])
+    reads = [e for e in range(lo, hi) if h.f[e] == H.F_READ and h.type[e] == H.T_OK and h.payload_len[e] > 4
+             and not (h.flags[e] & 1)]
+    h.payload_len[reads[-1]] -= 2
+    return h

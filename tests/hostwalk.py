@@ -37,3 +37,19 @@ def walk(h, model, eager_reads=True, max_configs=0):
         raise RuntimeError(f"jtb_hostwalk rc={rc}")
     return {"valid": max(valid) if n else 0, "configs": configs.value, "key_bytes": kw.value * 8,
             "shards": [{"valid": valid[s], "witness_index": wit[s], "previous_ok_index": prev[s]} for s in range(n)]}
+
+
+def walk_bfs(h, model, eager_reads=True, max_configs=0, width_cap=0):
+    """Breadth-first by depth with a visited set that lives for ONE level (the device level engine's rule)."""
+    ch = as_c_history(h)
+    n = h.n_shards
+    valid, wit, prev = (C.c_int32 * n)(), (C.c_int32 * n)(), (C.c_int32 * n)()
+    configs, kw, nl = C.c_ulonglong(0), C.c_int32(0), C.c_int(0)
+    widths = (C.c_ulonglong * max(1, width_cap))()
+    rc = lib().jtb_hostwalk_bfs(C.byref(ch), C.byref(model), int(eager_reads), C.c_ulonglong(max_configs), valid, wit,
+                                prev, C.byref(configs), C.byref(kw), widths, width_cap, C.byref(nl))
+    if rc != 0:
+        raise RuntimeError(f"jtb_hostwalk_bfs rc={rc}")
+    return {"valid": max(valid) if n else 0, "configs": configs.value, "key_bytes": kw.value * 8, "levels": nl.value,
+            "widths": list(widths[:min(width_cap, nl.value)]),
+            "shards": [{"valid": valid[s], "witness_index": wit[s], "previous_ok_index": prev[s]} for s in range(n)]}
