@@ -111,6 +111,12 @@ typedef struct jtb_model {
  * a scout can only ever report VALID (it found a linearization), so verdicts, witnesses and exhaustive
  * configuration counts are unaffected.  Set this flag to run the exhaustive search alone. */
 #define JTB_OPT_NO_SCOUTS 2
+/* Engine choice for jtb_check_linearizable.  Default (neither bit): the level-synchronous engine (csrc/jtb_level.cuh:
+ * breadth-first by depth, visited set local to a level, bounded memory) for histories without crashed (:info) ops,
+ * the work-list engine (csrc/jtb_wgl.cuh: depth-first locally, persistent visited table, scouts) otherwise.
+ * Verdict, witness and exhaustive configuration counts are identical; the bits force one engine. */
+#define JTB_OPT_ENGINE_LEVEL    4
+#define JTB_OPT_ENGINE_WORKLIST 8
 
 /* Options for a context.  Zero-initialise, then set what you need. */
 typedef struct jtb_opts {

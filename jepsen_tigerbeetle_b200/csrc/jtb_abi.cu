@@ -12,6 +12,7 @@
 
 #include "jtb_wgl.cuh"
 #include "jtb_search.cuh"
+#include "jtb_level.cuh"
 #include "jtb_scout.cuh"
 #include "jtb_scans.cuh"
 #include "jtb_table_bench.cuh"
@@ -35,6 +36,9 @@ struct jtb_ctx {
     // cached device buffers (grown on demand, reused across calls)
     DevBuf table, pool, rows, classes, cls_inv, ctrl, found, maxrank;
     DevBuf sc_init, sc_tables, sc_stacks, sc_ctl;   // scouts: initial entries, private tables, stacks, control words
+    DevBuf lv_ctrl, lv_buf[2];          // level engine: control block, the two level arrays
+    size_t table_dirty = ~(size_t)0;    // bytes at the start of `table` that may hold old slots (level engine clears only these)
+    int last_engine = 0;                // 0 work-list (visited table complete), 1 level (visited set is ephemeral)
     unsigned long long stats[20] = {0};
     unsigned long long last_configs = 0;  // configs of the previous search (sizes the next table)
     // what jtb_final_configs needs from the last search (its visited table is still in `table`)
@@ -135,6 +139,182 @@ int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid
     }
     ctx->err = "unsupported key width";
     return -1;
+}
+
+// the level engine (jtb_level.cuh): cooperative launch, every CTA resident (the levels are separated by grid barriers)
+template <int MODEL, int KW>
+int launch_level(jtb_ctx* ctx, const LvParams& p, int neg_ok, bool eager, int* grid_out) {
+    constexpr int EW = KW + (MODEL == JTB_MODEL_BANK ? 4 : 0);
+    const size_t smem = sizeof(LvScratch<KW, EW, MODEL == JTB_MODEL_BANK>) * LV_WARPS;
+    const void* k = eager ? (const void*)level_search_kernel<MODEL, KW, true> : (const void*)level_search_kernel<MODEL, KW, false>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LV_THREADS, smem));
+    if (per_sm < 1) { ctx->err = "level engine: the kernel does not fit on an SM"; return -1; }
+    per_sm = std::min(per_sm, JTB_LV_CTAS);
+    if (getenv("JTB_LV_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("JTB_LV_CTAS_PER_SM"))));
+    const int grid = ctx->opts.search_ctas ? std::min<int>((int)ctx->opts.search_ctas, ctx->n_sms * per_sm) : ctx->n_sms * per_sm;
+    *grid_out = grid;
+    LvParams pp = p;
+    int nk = neg_ok;
+    void* args[] = {&pp, &nk};
+    CK(cudaLaunchCooperativeKernel(k, dim3(grid), dim3(LV_THREADS), args, smem, ctx->stream));
+    return 0;
+}
+
+template <int MODEL>
+int launch_level_kw(jtb_ctx* ctx, int kw, const LvParams& p, int neg_ok, bool eager, int* grid_out) {
+    switch (kw) {
+    case 2: return launch_level<MODEL, 2>(ctx, p, neg_ok, eager, grid_out);
+    case 4: return launch_level<MODEL, 4>(ctx, p, neg_ok, eager, grid_out);
+    case 8: return launch_level<MODEL, 8>(ctx, p, neg_ok, eager, grid_out);
+    }
+    ctx->err = "unsupported key width";
+    return -1;
+}
+
+// ---- level engine, host side: buffers, (re)launch, growth ------------------------------------------------------
+// The search is ONE cooperative launch.  Only when a level outgrows the level arrays or the hash window does the kernel
+// stop (cause TABLE_FULL) with the level it could not finish intact in its input array; the host then allocates 4x
+// larger buffers, copies that one level over and relaunches from there.
+int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shards, const std::vector<int>& searchable,
+                 const std::vector<uint64_t>& init_entries, Ctrl& hc, double& kernel_s, uint64_t& configs, uint64_t& probes) {
+    const int KW = P.key_words;
+    const bool bank = m->kind == JTB_MODEL_BANK;
+    const int EW = KW + (bank ? 4 : 0);
+    const bool eager = !(ctx->opts.flags & JTB_OPT_NO_EAGER_READS);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t reserve = (size_t)4 << 30;
+    const size_t avail = ctx->table.cap + ctx->lv_buf[0].cap + ctx->lv_buf[1].cap + (free_b > reserve ? free_b - reserve : 0);
+    size_t table_bytes = ctx->opts.table_bytes ? ctx->opts.table_bytes
+                         : (getenv("JTB_LV_TABLE_MB") ? (size_t)atoll(getenv("JTB_LV_TABLE_MB")) << 20 : (size_t)1 << 30);
+    table_bytes = std::min(table_bytes, avail / 3);
+    size_t buf_bytes = getenv("JTB_LV_BUF_MB") ? (size_t)atoll(getenv("JTB_LV_BUF_MB")) << 20 : (size_t)512 << 20;
+    buf_bytes = std::max<size_t>(std::min(buf_bytes, avail / 3), init_entries.size() * 8 + 4096);
+    auto slots_of = [&](size_t bytes) { uint64_t s = 1; while (s * 2 * KW * 8 <= bytes) s <<= 1; return s; };
+    uint64_t table_slots = slots_of(std::max(table_bytes, ctx->table.cap));
+    auto ensure_table = [&](uint64_t slots) -> int {
+        const void* before = ctx->table.p;
+        if (ensure(ctx, ctx->table, slots * KW * 8)) return -1;
+        if (ctx->table.p != before) ctx->table_dirty = ~(size_t)0;
+        return 0;
+    };
+    if (ensure_table(table_slots)) return -1;
+    if (ensure(ctx, ctx->lv_buf[0], std::max(buf_bytes, ctx->lv_buf[0].cap)) || ensure(ctx, ctx->lv_buf[1], std::max(buf_bytes, ctx->lv_buf[1].cap)) ||
+        ensure(ctx, ctx->lv_ctrl, sizeof(LvCtrl)))
+        return -1;
+    uint64_t buf_cap = std::min(ctx->lv_buf[0].cap, ctx->lv_buf[1].cap) / ((size_t)EW * 8);
+    // only what an earlier search may have written is cleared (the rest of the table is still zero)
+    CK(cudaMemsetAsync(ctx->table.p, 0, std::min(ctx->table_dirty, (size_t)table_slots * KW * 8), ctx->stream));
+    ctx->table_dirty = 0;
+    LvCtrl lc;
+    std::memset(&lc, 0, sizeof lc);
+    lc.n_undecided = (int)searchable.size();
+    CK(cudaMemcpyAsync(ctx->lv_ctrl.p, &lc, sizeof lc, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->lv_buf[0].p, init_entries.data(), init_entries.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LvParams p{};
+    p.rows = (const int32_t*)ctx->rows.p;
+    p.classes = (const ClassRec*)ctx->classes.p;
+    p.cls_inv_pos = (const int32_t*)ctx->cls_inv.p;
+    p.ctrl = (LvCtrl*)ctx->lv_ctrl.p;
+    p.shard_found = (int*)ctx->found.p;
+    p.shard_max_rank = (int*)ctx->maxrank.p;
+    p.row_words = P.row_words;
+    p.sum_off = P.sum_off;
+    p.n_shards = n_shards;
+    p.max_configs = ctx->opts.max_configs;
+    p.time_budget_ns = (unsigned long long)ctx->opts.time_budget_ms * 1000000ull;
+    p.narrow_max = getenv("JTB_LV_NARROW") ? (uint32_t)atoi(getenv("JTB_LV_NARROW")) : (uint32_t)(LV_WARPS * 8);
+    p.slots_per_config = getenv("JTB_LV_SPC") ? (uint32_t)std::max(2, atoi(getenv("JTB_LV_SPC"))) : 16u;
+    p.min_slots = 1ull << 16;
+    std::memset(&p.init, 0, sizeof p.init);
+    p.init.n_in = searchable.size();
+    p.init.epoch = 1;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int attempts = 0, grid = 0;
+    unsigned long long max_window = 0, max_width = 0, narrow_levels = 0, max_probe = 0;
+    const double t_begin = now_s();
+    for (;;) {
+        ++attempts;
+        p.table = (uint64_t*)ctx->table.p;
+        p.table_slots = table_slots;
+        p.min_slots = std::min<uint64_t>(p.min_slots, table_slots);
+        p.buf[0] = (uint64_t*)ctx->lv_buf[0].p;
+        p.buf[1] = (uint64_t*)ctx->lv_buf[1].p;
+        p.buf_cap = buf_cap;
+        p.init.zeroed = table_slots;
+        if (ctx->opts.time_budget_ms) {   // what is left of the budget for this launch
+            const double left = ctx->opts.time_budget_ms * 1e-3 - (now_s() - t_begin);
+            p.time_budget_ns = (unsigned long long)(std::max(left, 1e-3) * 1e9);
+        }
+        int rc;
+        if (bank) rc = launch_level_kw<JTB_MODEL_BANK>(ctx, KW, p, m->negative_balances_ok, eager, &grid);
+        else if (m->kind == JTB_MODEL_SET) rc = launch_level<JTB_MODEL_SET, 2>(ctx, p, 0, eager, &grid);
+        else rc = launch_level_kw<JTB_MODEL_CAS_REGISTER>(ctx, KW, p, 0, eager, &grid);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&lc, ctx->lv_ctrl.p, sizeof lc, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        probes += lc.probes;
+        max_window = std::max(max_window, lc.max_window);
+        max_width = std::max(max_width, lc.max_width);
+        max_probe = std::max(max_probe, lc.max_probe_len);
+        narrow_levels += lc.narrow_levels;
+        ctx->table_dirty = std::max(ctx->table_dirty, (size_t)std::max<uint64_t>(lc.max_window, p.min_slots) * KW * 8);
+        if (!(lc.fin.stop == 2 && lc.fin.cause == JTB_CAUSE_TABLE_FULL)) break;
+        // ---- a level outgrew the arrays or the window: 4x of both, carry the unfinished level over -------------
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t have = ctx->table.cap + ctx->lv_buf[0].cap + ctx->lv_buf[1].cap;
+        const size_t room = have + (free_b > reserve ? free_b - reserve : 0);
+        const size_t new_table = std::min<size_t>((size_t)table_slots * KW * 8 * 4, (size_t)64 << 30);
+        const size_t new_buf = std::min(ctx->lv_buf[0].cap, ctx->lv_buf[1].cap) * 4;
+        // peak while the unfinished level is copied over: its old array + the two new arrays + the new table
+        if (new_table + 2 * new_buf + ctx->lv_buf[lc.fin.in_idx].cap > room) break;
+        const int ii = lc.fin.in_idx;
+        if (ctx->lv_buf[ii ^ 1].p) { CK(cudaFree(ctx->lv_buf[ii ^ 1].p)); ctx->lv_buf[ii ^ 1] = DevBuf(); }
+        if (ctx->table.p) { CK(cudaFree(ctx->table.p)); ctx->table = DevBuf(); }
+        DevBuf grown;
+        if (ensure(ctx, grown, new_buf)) return -1;
+        CK(cudaMemcpyAsync(grown.p, ctx->lv_buf[ii].p, (size_t)lc.fin.n_in * EW * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(ctx->lv_buf[ii].p));
+        ctx->lv_buf[ii] = grown;
+        if (ensure(ctx, ctx->lv_buf[ii ^ 1], new_buf)) return -1;
+        table_slots = slots_of(new_table);
+        if (ensure_table(table_slots)) return -1;
+        CK(cudaMemsetAsync(ctx->table.p, 0, (size_t)table_slots * KW * 8, ctx->stream));
+        ctx->table_dirty = 0;
+        buf_cap = new_buf / ((size_t)EW * 8);
+        // resume at the level that did not fit
+        LvState r = lc.fin;
+        r.stop = 0; r.cause = 0; r.boost = 0; r.attempt = 0; r.epoch = 1;
+        p.init = r;
+        const int undecided = lc.n_undecided;
+        std::memset(&lc, 0, sizeof lc);
+        lc.n_undecided = undecided;
+        CK(cudaMemcpyAsync(ctx->lv_ctrl.p, &lc, sizeof lc, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    kernel_s = ms * 1e-3;
+    configs = lc.fin.total;
+    std::memset(&hc, 0, sizeof hc);
+    hc.stop = lc.fin.stop;
+    hc.cause = lc.fin.cause;
+    hc.configs = lc.fin.total;
+    hc.probes = probes;
+    hc.n_undecided = lc.n_undecided;
+    unsigned long long* st = ctx->stats;
+    st[0] = configs; st[1] = probes; st[2] = lc.fin.level + 1; st[3] = max_width; st[4] = narrow_levels; st[5] = 0;
+    st[6] = max_probe; st[7] = max_window; st[8] = (unsigned long long)grid; st[9] = buf_cap;
+    st[10] = (unsigned long long)attempts; st[11] = (unsigned long long)(ms * 1e3);
+    st[12] += init_entries.size() * 8 + sizeof(LvCtrl) + (size_t)n_shards * 4;
+    st[13] = (unsigned long long)attempts * sizeof(LvCtrl) + (size_t)n_shards * 8;
+    st[14] = (unsigned long long)attempts;
+    st[19] = 1;   // engine: level
+    return 0;
 }
 
 // Stops the scouts on every way out of a search (they only end on their own when their budget is spent).
@@ -261,7 +441,8 @@ void jtb_destroy(jtb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     DevBuf* bufs[] = {&ctx->table, &ctx->pool, &ctx->rows, &ctx->classes, &ctx->cls_inv, &ctx->ctrl, &ctx->found,
-                      &ctx->maxrank, &ctx->sc_init, &ctx->sc_tables, &ctx->sc_stacks, &ctx->sc_ctl};
+                      &ctx->maxrank, &ctx->sc_init, &ctx->sc_tables, &ctx->sc_stacks, &ctx->sc_ctl, &ctx->lv_ctrl,
+                      &ctx->lv_buf[0], &ctx->lv_buf[1]};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -275,10 +456,9 @@ void jtb_destroy(jtb_ctx* ctx) {
 const char* jtb_last_error(const jtb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 
 // -------------------------------------------------------------------------------------------------
-int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, jtb_lin_shard* shards,
-                           jtb_lin_result* out) {
-    if (!ctx) return -1;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+// force_engine: 0 = by options / history, 1 = level, 2 = work list
+static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, jtb_lin_shard* shards,
+                          jtb_lin_result* out, int force_engine) {
     const double t_start = now_s();
     ctx->fc.valid = false;
     CK(cudaSetDevice(ctx->device));
@@ -329,12 +509,35 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     Ctrl hc;
     std::memset(&hc, 0, sizeof hc);
     std::vector<int> h_found(n_shards, 0), h_max(n_shards, 0);
+    uint64_t fc_n_slots = 0;
+    bool scout_only_run = false;
     if (!searchable.empty()) {
         if (upload(ctx, ctx->rows, P.rows) || upload(ctx, ctx->classes, P.classes) || upload(ctx, ctx->cls_inv, P.cls_inv_pos))
             return -1;
         if (ensure(ctx, ctx->ctrl, sizeof(Ctrl)) || ensure(ctx, ctx->found, n_shards * sizeof(int)) ||
             ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
             return -1;
+        // ---- engine: level-synchronous sweep (jtb_level.cuh) or work list (jtb_wgl.cuh / jtb_search.cuh) ----------
+        bool use_level = P.max_nc == 0;   // crashed ops: the depth-first work list + scouts find linearizations sooner
+        if (ctx->opts.flags & JTB_OPT_ENGINE_LEVEL) use_level = true;
+        if (ctx->opts.flags & JTB_OPT_ENGINE_WORKLIST) use_level = false;
+        if (const char* en = getenv("JTB_ENGINE")) use_level = std::strcmp(en, "level") == 0;
+        if (force_engine) use_level = force_engine == 1;
+        if (P.n_ranks >= LV_MAX_RANKS || P.max_nc > 64) use_level = false;   // epoch tag bits / class mask width
+        ctx->stats[19] = 0;
+        if (use_level) {
+            CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));
+            for (int s = 0; s < n_shards; ++s) h_max[s] = (int)P.rank_base[s];
+            CK(cudaMemcpyAsync(ctx->maxrank.p, h_max.data(), n_shards * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            if (int rc = search_level(ctx, m, P, n_shards, searchable, init_entries, hc, kernel_s, configs, probes)) return rc;
+            CK(cudaMemcpyAsync(h_found.data(), ctx->found.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_max.data(), ctx->maxrank.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->last_configs = configs;
+            ctx->last_engine = 1;
+        } else {
+        ctx->last_engine = 0;
+        ctx->table_dirty = ~(size_t)0;   // the work-list engine fills the table
         // CTA deque / grid.  Two interchangeable search kernels: "tpc" (one THREAD per configuration, jtb_search.cuh:
         // throughput) and "warp" (one WARP per configuration, jtb_wgl.cuh: every child of a configuration probed in
         // the same round trip).  Default tpc; env JTB_KERNEL=warp|tpc overrides (A/B measurements).
@@ -570,6 +773,8 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             if (scouts.stop()) { free_tmp(); return -1; }
             CK(cudaMemcpyAsync(sc_ctl, ctx->sc_ctl.p, sizeof sc_ctl, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        fc_n_slots = n_slots;
+        scout_only_run = scout_only;
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         CK(cudaMemcpyAsync(h_found.data(), ctx->found.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_max.data(), ctx->maxrank.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -592,6 +797,7 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             st[14] = (unsigned long long)((scout_only ? 0 : attempts) + 3 * (attempts - 1) + (n_scouts ? 1 : 0));  // search + compact/rehash/re-arm + scouts
             st[15] = sc_ctl[2]; st[16] = sc_ctl[3]; st[17] = sc_ctl[4]; st[18] = (unsigned long long)n_scouts;
         }
+        }   // engine
         if (hc.stop == 2 && hc.cause == CAUSE_RING_FULL) hc.cause = JTB_CAUSE_BUDGET;
         if (hc.overflow) {   // a ring slot was overwritten before it was consumed: no verdict may be derived from this search
             hc.stop = 2;
@@ -616,11 +822,11 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
             shards[0].configs_explored = configs;
             shards[0].probes = probes;
         }
-        ctx->fc.valid = !scout_only;
+        ctx->fc.valid = !scout_only_run;
         ctx->fc.n_events = h->n_events;
         ctx->fc.n_shards = n_shards;
         ctx->fc.kw = KW;
-        ctx->fc.n_slots = n_slots;
+        ctx->fc.n_slots = fc_n_slots;
         ctx->fc.max_rank = h_max;
         ctx->fc.verdict.assign(n_shards, JTB_UNKNOWN);
         for (int s = 0; s < n_shards; ++s) ctx->fc.verdict[s] = shards[s].valid;
@@ -637,6 +843,13 @@ int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* 
     return 0;
 }
 
+int jtb_check_linearizable(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, jtb_lin_shard* shards,
+                           jtb_lin_result* out) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return check_lin_impl(ctx, h, m, shards, out, 0);
+}
+
 // -------------------------------------------------------------------------------------------------
 // knossos :configs for an INVALID shard: the visited configurations stuck at the witness
 int jtb_final_configs(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, int32_t shard, jtb_final_config* out,
@@ -644,6 +857,13 @@ int jtb_final_configs(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, in
     if (!ctx) return -1;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
+    if (ctx->fc.valid && ctx->last_engine == 1 && h->n_events == ctx->fc.n_events && h->n_shards == ctx->fc.n_shards) {
+        // the level engine keeps no visited set: search again with the work-list engine, whose table holds every
+        // visited configuration (same verdict and witness; only asked for after an INVALID verdict)
+        std::vector<jtb_lin_shard> tmp_shards((size_t)h->n_shards);
+        jtb_lin_result tmp_out;
+        if (int rc = check_lin_impl(ctx, h, m, tmp_shards.data(), &tmp_out, 2)) return rc;
+    }
     if (!ctx->fc.valid || h->n_events != ctx->fc.n_events || h->n_shards != ctx->fc.n_shards || shard < 0 ||
         shard >= h->n_shards) {
         ctx->err = "jtb_final_configs: call it directly after jtb_check_linearizable on the same history";

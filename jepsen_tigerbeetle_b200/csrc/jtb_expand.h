@@ -68,6 +68,7 @@ struct ExpandTables {
     const ClassRec* classes;
     const int32_t* cls_inv_pos;
     int row_words;
+    int sum_off;   // offset of the per-slot summary words in a row (jtb_prep.h); 0 = do not use them
 };
 
 template <int KW>
@@ -83,6 +84,7 @@ struct Expander {
     static constexpr int SW = MODEL == JTB_MODEL_BANK ? 12 : MODEL == JTB_MODEL_SET ? 8 : 4;  // = slot_words(MODEL)
     static constexpr bool BANK = MODEL == JTB_MODEL_BANK;
     static constexpr bool REG = MODEL == JTB_MODEL_REGISTER || MODEL == JTB_MODEL_CAS_REGISTER;
+    static constexpr bool SET = MODEL == JTB_MODEL_SET;
 
     uint64_t w[KW];
     int32_t bal[8];
@@ -142,6 +144,29 @@ struct Expander {
                 for (int i = 0; i < 8; ++i) balhash += (uint32_t)bal[i] * bank_hash_c(i);
             }
         }
+        // Reads the summary words decide (one contiguous array, all loads independent): only the reads whose summary
+        // matches the state are looked at in their cell (bank: exact balances; eager: invocation position).
+        if constexpr (!SET) {
+            const uint64_t fastm = T.sum_off ? (rds & u64_of(h4.z, h4.w)) : 0ull;
+            if (fastm) {
+                const int32_t* sum = row + T.sum_off;
+                const int32_t want = BANK ? (int32_t)balhash : reg;
+                uint64_t match = 0;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    if ((fastm >> (4 * g)) & 0xfull) {
+                        const I4 v = ld_i4(sum + 4 * g);
+                        uint32_t mm = (v.x == want) | ((v.y == want) << 1) | ((v.z == want) << 2) | ((v.w == want) << 3);
+                        if constexpr (REG)
+                            mm |= (v.x == JTB_NIL) | ((v.y == JTB_NIL) << 1) | ((v.z == JTB_NIL) << 2) | ((v.w == JTB_NIL) << 3);
+                        match |= (uint64_t)mm << (4 * g);
+                    }
+                }
+                match &= fastm;
+                if constexpr (REG && !EAGER) { rd_ok |= match; match = 0; }   // the summary is exact: nothing left to look at
+                rds = (rds & ~fastm) | match;
+            }
+        }
         uint32_t best_inv = 0xffffffffu;
         int best_t = -1;
         while (rds) {
@@ -182,67 +207,91 @@ struct Expander {
         return v;
     }
 
+    // ---- one child at a time, addressable (the level engine hands every child of a warp's 32 configurations to its
+    //      own lane; next() below walks the same two lists in order) -----------------------------------------------
+    // child that linearizes the op in open slot t (t must be a bit of `todo` as begin() computed it)
+    // lazy_op (bank, negative balances allowed): a transfer never fails and the key does not depend on it, so its
+    // record is not loaded here; the caller fetches it with load_transfer() only for the children that turn out NEW
+    // (ch.d == -1 marks "not loaded")
+    JTB_HD bool child_slot(const ExpandTables& T, int t, bool neg_ok, Child<KW>& ch, bool lazy_op = false) const {
+        int32_t creg = reg;
+        ch.amt = 0; ch.d = 0; ch.c = 0;
+        if (!((rd_ok >> t) & 1ull)) {
+            if (BANK && lazy_op && neg_ok) {
+                ch.d = -1;
+            } else {
+                const I4 op = ld_i4(row + ROW_EXTRA + t * SW);
+                if constexpr (REG) {
+                    if ((op.x & 0xff) == JTB_F_WRITE) creg = op.y;
+                    else { if (reg != op.y) return false; creg = op.z; }   // cas
+                } else if constexpr (BANK) {
+                    ch.amt = op.y; ch.d = op.z; ch.c = op.w;
+                    if (!neg_ok && balance_of(op.z) - op.y < 0) return false;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KW; ++i) ch.w[i] = w[i];
+        int cgj = gj;
+        if (t == rslot) advance(T, ch.w[1], cgj);
+        else ch.w[1] |= 1ull << t;
+        ch.w[0] = XKEY_VALID | ((uint64_t)(uint32_t)cgj << 32) | (REG ? (uint64_t)(uint32_t)creg : 0ull);
+        ch.cgj = cgj;
+        ch.done = cgj >= gj_end;
+        return true;
+    }
+
+    JTB_HD void load_transfer(int t, Child<KW>& ch) const {
+        const I4 op = ld_i4(row + ROW_EXTRA + t * SW);
+        ch.amt = op.y; ch.d = op.z; ch.c = op.w;
+    }
+
+    // child that linearizes the next member of crashed-op class ci of the shard (0 <= ci < ncls)
+    JTB_HD bool child_class(const ExpandTables& T, int ci, bool neg_ok, Child<KW>& ch) const {
+        const int32_t* q = reinterpret_cast<const int32_t*>(T.classes + cls_base + ci);
+        const I4 b = ld_i4(q + 4);   // first, n, word, shift | width << 8
+        const int shift = b.w & 0xff, width = b.w >> 8;
+        uint64_t field = 0;
+#pragma unroll
+        for (int i = 1; i < KW; ++i) if (i == b.z) field = w[i];
+        const int count = (int)((field >> shift) & ((1ull << width) - 1));
+        if (count >= b.y) return false;                                  // the whole class is consumed
+        if (ld_i32(T.cls_inv_pos + b.x + count) >= fr_pos) return false;  // its next member is not invoked yet
+        const I4 op = ld_i4(q);
+        if (op.x & OP_IMPOSSIBLE) return false;
+        int32_t creg = reg;
+        ch.amt = 0; ch.d = 0; ch.c = 0;
+        if constexpr (REG) {
+            const int f = op.x & 0xff;
+            if (f == JTB_F_WRITE) creg = op.y;
+            else if (f == JTB_F_CAS) { if (reg != op.y) return false; creg = op.z; }
+            else if (!(op.y == JTB_NIL || op.y == reg)) return false;   // (crashed reads are dropped by the prep)
+        } else if constexpr (BANK) {
+            if ((op.x & 0xff) != JTB_F_TRANSFER) return false;
+            ch.amt = op.y; ch.d = op.z; ch.c = op.w;
+            if (!neg_ok && balance_of(op.z) - op.y < 0) return false;
+        } else {
+            if ((op.x & 0xff) != JTB_F_ADD) return false;
+        }
+#pragma unroll
+        for (int i = 0; i < KW; ++i) ch.w[i] = w[i];
+#pragma unroll
+        for (int i = 1; i < KW; ++i) if (i == b.z) ch.w[i] += 1ull << shift;
+        ch.w[0] = XKEY_VALID | ((uint64_t)(uint32_t)gj << 32) | (REG ? (uint64_t)(uint32_t)creg : 0ull);
+        ch.cgj = gj;
+        ch.done = false;
+        return true;
+    }
+
     JTB_HD bool next(const ExpandTables& T, bool neg_ok, Child<KW>& ch) {
         while (todo) {
             const int t = ctz64(todo);
             todo &= todo - 1;
-            int32_t creg = reg;
-            ch.amt = 0; ch.d = 0; ch.c = 0;
-            if (!((rd_ok >> t) & 1ull)) {
-                const I4 op = ld_i4(row + ROW_EXTRA + t * SW);
-                if constexpr (REG) {
-                    if ((op.x & 0xff) == JTB_F_WRITE) creg = op.y;
-                    else { if (reg != op.y) continue; creg = op.z; }   // cas
-                } else if constexpr (BANK) {
-                    ch.amt = op.y; ch.d = op.z; ch.c = op.w;
-                    if (!neg_ok && balance_of(op.z) - op.y < 0) continue;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < KW; ++i) ch.w[i] = w[i];
-            int cgj = gj;
-            if (t == rslot) advance(T, ch.w[1], cgj);
-            else ch.w[1] |= 1ull << t;
-            ch.w[0] = XKEY_VALID | ((uint64_t)(uint32_t)cgj << 32) | (REG ? (uint64_t)(uint32_t)creg : 0ull);
-            ch.cgj = cgj;
-            ch.done = cgj >= gj_end;
-            return true;
+            if (child_slot(T, t, neg_ok, ch)) return true;
         }
         while (cls_i < ncls) {
-            const int32_t* q = reinterpret_cast<const int32_t*>(T.classes + cls_base + cls_i);
-            ++cls_i;
-            const I4 b = ld_i4(q + 4);   // first, n, word, shift | width << 8
-            const int shift = b.w & 0xff, width = b.w >> 8;
-            uint64_t field = 0;
-#pragma unroll
-            for (int i = 1; i < KW; ++i) if (i == b.z) field = w[i];
-            const int count = (int)((field >> shift) & ((1ull << width) - 1));
-            if (count >= b.y) continue;                                  // the whole class is consumed
-            if (ld_i32(T.cls_inv_pos + b.x + count) >= fr_pos) continue;  // its next member is not invoked yet
-            const I4 op = ld_i4(q);
-            if (op.x & OP_IMPOSSIBLE) continue;
-            int32_t creg = reg;
-            ch.amt = 0; ch.d = 0; ch.c = 0;
-            if constexpr (REG) {
-                const int f = op.x & 0xff;
-                if (f == JTB_F_WRITE) creg = op.y;
-                else if (f == JTB_F_CAS) { if (reg != op.y) continue; creg = op.z; }
-                else if (!(op.y == JTB_NIL || op.y == reg)) continue;   // (crashed reads are dropped by the prep)
-            } else if constexpr (BANK) {
-                if ((op.x & 0xff) != JTB_F_TRANSFER) continue;
-                ch.amt = op.y; ch.d = op.z; ch.c = op.w;
-                if (!neg_ok && balance_of(op.z) - op.y < 0) continue;
-            } else {
-                if ((op.x & 0xff) != JTB_F_ADD) continue;
-            }
-#pragma unroll
-            for (int i = 0; i < KW; ++i) ch.w[i] = w[i];
-#pragma unroll
-            for (int i = 1; i < KW; ++i) if (i == b.z) ch.w[i] += 1ull << shift;
-            ch.w[0] = XKEY_VALID | ((uint64_t)(uint32_t)gj << 32) | (REG ? (uint64_t)(uint32_t)creg : 0ull);
-            ch.cgj = gj;
-            ch.done = false;
-            return true;
+            const int ci = cls_i++;
+            if (child_class(T, ci, neg_ok, ch)) return true;
         }
         return false;
     }

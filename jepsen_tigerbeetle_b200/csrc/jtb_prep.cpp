@@ -374,7 +374,8 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
     out.key_words = key_words;
     // ---- pass 3: tables -----------------------------------------------------------------------
     const int SW = slot_words(m->kind);
-    const int RW = ROW_EXTRA + out.S_pad * SW;
+    out.sum_off = ROW_EXTRA + out.S_pad * SW;
+    const int RW = out.sum_off + out.S_pad;
     out.row_words = RW;
     out.rank_base.assign(n_shards + 1, 0);
     for (int s = 0; s < n_shards; ++s) out.rank_base[s + 1] = out.rank_base[s] + (int64_t)tmp[s].rets.size();
@@ -463,15 +464,24 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
         // slot masks of every row (after the set model has marked its impossible reads)
         for (int j = 0; j < R; ++j) {
             int32_t* row = &out.rows[(size_t)(base + j) * RW];
-            uint64_t occ = 0, rd = 0;
+            uint64_t occ = 0, rd = 0, fast = 0;
             for (int sl = 0; sl < out.S_pad; ++sl) {
-                const int32_t x = row[ROW_EXTRA + sl * SW];
+                const int32_t* cell = row + ROW_EXTRA + sl * SW;
+                const int32_t x = cell[0];
                 if (x < 0 || (x & OP_IMPOSSIBLE)) continue;
                 occ |= 1ull << sl;
-                if ((x & 0xff) == JTB_F_READ) rd |= 1ull << sl;
+                if ((x & 0xff) != JTB_F_READ) continue;
+                rd |= 1ull << sl;
+                if (m->kind == JTB_MODEL_BANK) {
+                    if (x & OP_HASHED) { fast |= 1ull << sl; row[out.sum_off + sl] = cell[2]; }
+                } else if (m->kind != JTB_MODEL_SET) {
+                    fast |= 1ull << sl;
+                    row[out.sum_off + sl] = cell[1];
+                }
             }
             std::memcpy(row + 14, &occ, 8);
             std::memcpy(row + 16, &rd, 8);
+            std::memcpy(row + 18, &fast, 8);
         }
     }
     return true;

@@ -57,13 +57,17 @@ struct ClassRec {
 //   [13]       slot of this rank's own op
 //   [14..15]   u64 mask of the slots that hold a linearizable op at this return (empty / impossible ops excluded)
 //   [16..17]   u64 mask of those slots whose op is a READ (never changes the model state)
-//   [18..19]   pad
+//   [18..19]   u64 mask of the READ slots that the summary word below decides (bank: reads covering every account,
+//              summary = hash of the expected balances, equal hash still verified against the cell; register /
+//              cas-register: every read, summary = the expected value, exact)
 //   [20 + t*SW, 20 + (t+1)*SW)   the op occupying open-op slot t at that return event, INLINE:
 //        words 0..3  OpRec (x = -1: slot empty)
 //        bank  (SW = 12): words 4..11 = the 8 balances a read expects (by account slot; op.y = care mask);
 //                         word 4 of a TRANSFER = its invocation position
 //        set   (SW = 8):  words 4..7  = (need, care) u64 pair of a read AT THIS RANK:
 //                         consistent <=> (key word1 & care) == need
+//   [20 + S_pad*SW, 20 + S_pad*SW + S_pad)   one SUMMARY word per slot (see [18..19]): a thread decides every
+//        candidate read of a configuration from this one contiguous array instead of one cell load per read
 constexpr int ROW_EXTRA = 20;
 inline int slot_words(int model) { return model == JTB_MODEL_BANK ? 12 : model == JTB_MODEL_SET ? 8 : 4; }
 constexpr int OP_EMPTY = -1;
@@ -73,7 +77,8 @@ struct Prepared {
     int key_words = 2;       // 64-bit words per key: 2, 4 or 8
     int model = 0;
     int64_t n_ranks = 0;     // total completed ops over all searchable shards
-    int row_words = 0;                // ROW_EXTRA + S_pad * slot_words(model)
+    int row_words = 0;                // ROW_EXTRA + S_pad * slot_words(model) + S_pad
+    int sum_off = 0;                  // ROW_EXTRA + S_pad * slot_words(model): offset of the summary words in a row
     std::vector<int32_t> rows;        // n_ranks * row_words
     std::vector<OpRec> ops;           // global op table (host side only: copied inline into rows)
     std::vector<int32_t> read_bal;    // bank: 8 per read (host side only)

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(TPC_THREADS, JTB_TPC_CTAS) wgl_tpc_kernel(cons
     const unsigned cap_mask = p.deque_cap - 1;
     const unsigned high = p.deque_cap / 2;   // donate the oldest entries beyond this; overflow goes to the ring
     ExpandTables T;
-    T.rows = p.rows; T.classes = p.classes; T.cls_inv_pos = p.cls_inv_pos; T.row_words = p.row_words;
+    T.rows = p.rows; T.classes = p.classes; T.cls_inv_pos = p.cls_inv_pos; T.row_words = p.row_words; T.sum_off = 0;
 
     if (tid == 0) {
         sh.stop = 0; sh.top = sh.bot = 0;

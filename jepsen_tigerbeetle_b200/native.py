@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("JTB_LIB_PATH") or os.path.join(_HERE, "libjtb_check.s
 CSRC = os.path.join(_HERE, "csrc")
 _SOURCES = ["jtb_abi.cu", "jtb_prep.cpp", "jtb_multi.cpp"]
 _DEPS = _SOURCES + ["jtb_prep.h", "jtb_expand.h", "jtb_wgl.cuh", "jtb_search.cuh", "jtb_scout.cuh", "jtb_scans.cuh",
-                    "jtb_table_bench.cuh"]
+                    "jtb_table_bench.cuh", "jtb_level.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
@@ -96,9 +96,11 @@ class Context:
 
     def __init__(self, device: int = 0, table_bytes: int = 0, max_configs: int = 0,
                  time_budget_ms: int = 0, search_ctas: int = 0, eager_reads: bool = True,
-                 scouts: bool = True) -> None:
+                 scouts: bool = True, engine: str = "auto") -> None:
+        """engine: "auto" (level engine for histories without crashed ops, work list otherwise), "level", "worklist"."""
         L = lib()
         flags = (0 if eager_reads else abi.OPT_NO_EAGER_READS) | (0 if scouts else abi.OPT_NO_SCOUTS)
+        flags |= {"auto": 0, "level": abi.OPT_ENGINE_LEVEL, "worklist": abi.OPT_ENGINE_WORKLIST}[engine]
         opts = abi.COpts(device, flags, table_bytes, max_configs, time_budget_ms, search_ctas)
         self._h = L.jtb_create(C.byref(opts))
         if not self._h:
@@ -188,7 +190,7 @@ class Context:
         names = ["configs", "probes", "expansions", "ring_tail", "ring_head", "idle_polls",
                  "max_probe_len", "table_slots", "grid", "ring_entries", "attempts", "kernel_us",
                  "h2d_bytes", "d2h_bytes", "kernel_launches", "scout_steps", "scout_configs",
-                 "scout_decided", "scouts"]
+                 "scout_decided", "scouts", "engine_level"]
         return {n: int(out[i]) for i, n in enumerate(names)}
 
     # ---- K2 microbenchmark ----------------------------------------------------------------------

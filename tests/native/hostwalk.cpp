@@ -24,7 +24,8 @@ struct KeyHash {
 template <int MODEL, int KW, bool EAGER>
 void walk(const Prepared& P, const jtb_model* m, unsigned long long max_configs, int n_shards, int32_t* valid,
           int32_t* witness, int32_t* prev_ok, unsigned long long* configs_out) {
-    ExpandTables T{P.rows.data(), P.classes.data(), P.cls_inv_pos.data(), P.row_words};
+    const bool use_summary = false;   // the work-list kernels decide candidate reads cell by cell
+    ExpandTables T{P.rows.data(), P.classes.data(), P.cls_inv_pos.data(), P.row_words, use_summary ? P.sum_off : 0};
     struct Entry { uint64_t w[KW]; int32_t bal[8]; };
     unsigned long long configs = 0;
     bool budget_hit = false;
@@ -82,7 +83,8 @@ template <int MODEL, int KW, bool EAGER>
 void walk_bfs(const Prepared& P, const jtb_model* m, unsigned long long max_configs, int n_shards, int32_t* valid,
               int32_t* witness, int32_t* prev_ok, unsigned long long* configs_out, unsigned long long* widths, int cap,
               int* n_levels_out) {
-    ExpandTables T{P.rows.data(), P.classes.data(), P.cls_inv_pos.data(), P.row_words};
+    const bool use_summary = true;    // the level engine decides them from the rows' summary words
+    ExpandTables T{P.rows.data(), P.classes.data(), P.cls_inv_pos.data(), P.row_words, use_summary ? P.sum_off : 0};
     struct Entry { uint64_t w[KW]; int32_t bal[8]; };
     std::vector<Entry> cur, nxt;
     std::vector<int> max_rank(n_shards);

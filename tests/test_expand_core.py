@@ -100,3 +100,35 @@ def test_multi_key(oracle_mod):
                                            stale_read=stale))
         m = model_for("cas-register")
         compare(hostwalk.walk(h, m), oracle_mod.check_linearizable(h, m, 3, n_threads=4, eager_reads=True), counts=False)
+
+
+# ---- the level engine's rule on the CPU: breadth-first by depth, visited set local to a level, candidate reads decided
+#      from the rows' summary words (csrc/jtb_level.cuh runs exactly this expansion core) --------------------------------
+@pytest.mark.parametrize("name,model,text,expect,witness", kat.ALL_LIN_KATS, ids=[k[0] for k in kat.ALL_LIN_KATS])
+def test_level_walk_kats(oracle_mod, name, model, text, expect, witness):
+    h = H.flatten_ops(kat.ops(text), model)
+    for eager in (True, False):
+        w = hostwalk.walk_bfs(h, model_for(model), eager_reads=eager)
+        assert w["valid"] == expect
+        compare(w, oracle_mod.check_linearizable(h, model_for(model), 3, eager_reads=eager))
+
+
+@pytest.mark.parametrize("eager", [True, False])
+@pytest.mark.parametrize("model", ["register", "cas-register", "bank", "set"])
+def test_level_walk_random_small(oracle_mod, model, eager):
+    for seed in range(40):
+        spec = synth.SynthSpec(model, n_ops=60, n_clients=4, seed=seed, p_info=0.1 if seed % 2 else 0.0,
+                               stale_read=seed % 3 != 0, stale_by=3 + seed % 5, n_values=3)
+        h = synth.generate(spec)
+        m = model_for(model)
+        compare(hostwalk.walk_bfs(h, m, eager_reads=eager), oracle_mod.check_linearizable(h, m, 3, eager_reads=eager))
+
+
+def test_level_walk_counts_on_a_wide_bank_history(oracle_mod):
+    """5.8 M configurations, levels up to 577 k wide: a per-level visited set finds every duplicate."""
+    h = synth.generate(synth.SynthSpec("bank", 3000, 32, 2, tau_think_ns=20e6, stale_read=True))
+    m = model_for("bank")
+    w = hostwalk.walk_bfs(h, m, eager_reads=True, width_cap=4000)
+    o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True)
+    compare(w, o)
+    assert w["levels"] > 2000 and max(w["widths"]) > 5000

@@ -345,7 +345,7 @@ def test_pause_resume_on_ring_and_table_growth(oracle_mod, monkeypatch):
     for eager in (True, False):
         o = oracle_mod.check_linearizable(h, m, 3, eager_reads=eager)
         assert o["valid"] == H.INVALID
-        with native.Context(eager_reads=eager) as ctx:
+        with native.Context(eager_reads=eager, engine="worklist") as ctx:
             g = ctx.check_linearizable(h, m)
             st = ctx.stats()
         same_verdict(g, o)
