@@ -2,9 +2,13 @@
 """bench.py — the reference's headline metric on the reference's headline config.
 
 metric   : configs explored/sec (BASELINE.json; time-to-verdict reported beside it)
-workload : BASELINE config #3 — 10k-op bank-transfer history, 32 clients, single B200
-           (synthetic, linearizable by construction; tau_op 10 ms, tau_think 5 ms, seed 1).
+workload : BASELINE config #3 exactly as SURVEY.md 8(d) writes it — 10k-op bank-transfer history, 32 clients,
+           tau_op 10 ms, tau_think 0 (every client always has an op in flight: the hardest setting), linearizable by
+           construction, seed 1; searched in the Knossos-exact space (7.1e9 configurations).
            One "step" = one complete linearizability check of that history through the C ABI.
+           The CPU reference cannot finish this instance (it would need > 100 GB for its cache and ~1 h), so both
+           arms also carry `verdict_to_verdict`: the same history shape at tau_think 5 ms (1.9e8 configurations),
+           which both arms run to the verdict (round 1's headline instance).
            N > 1 : one such history per GPU as independent keys (ledgers), sharded by key, verdicts
            merged with one NCCL all_reduce(MAX)  -> weak scaling.
 
@@ -45,10 +49,16 @@ METRIC = "configs explored/sec (time-to-verdict alongside) on 10k-op/32-client b
 UNIT = "configs/s"
 
 
-def workload(seed, args):
-    spec = synth.SynthSpec("bank", args.ops, args.clients, seed, tau_think_ns=args.think_ms * 1e6,
-                           stale_read=args.invalid)
+def workload(seed, args, think_ms=None):
+    spec = synth.SynthSpec("bank", args.ops, args.clients, seed,
+                           tau_think_ns=(args.think_ms if think_ms is None else think_ms) * 1e6, stale_read=args.invalid)
     return synth.generate(spec)
+
+
+def v2v_workload_name(args):
+    return (f"C3 bank-transfer history: {args.ops} ops, {args.clients} clients, tau_op 10 ms, tau_think "
+            f"{args.v2v_think_ms} ms, seed 1, {'one stale read (invalid)' if args.invalid else 'linearizable (valid)'}, "
+            "Knossos-exact space")
 
 
 def config_block(args, n_gpus):
@@ -56,8 +66,9 @@ def config_block(args, n_gpus):
                         f"tau_op 10 ms, tau_think {args.think_ms} ms, seed 1+key, "
                         f"{'one stale read (invalid)' if args.invalid else 'linearizable (valid)'}",
             "keys": n_gpus, "sharding": "one key (ledger) per GPU" if n_gpus > 1 else "single key",
-            "l2": "visited table (>= 1 GiB, cleared every step) and 192 MiB work ring exceed the 126 MB L2",
-            "model": "bank", "table": "16 B slots, linear probing, load <= 0.5",
+            "l2": "level windows up to 4 GiB and level arrays up to 2 GiB (45 M configurations per level) exceed the 126 MB L2",
+            "model": "bank", "table": "16 B slots, linear probing, per-level window of 16 slots per configuration",
+            "engine": "level-synchronous (csrc/jtb_level.cuh)",
             "search_space": "eager-read reduction (product default)" if args.eager_reads else
                             "Knossos-exact (JTB_OPT_NO_EAGER_READS): the same configurations the CPU reference visits"}
 
@@ -232,14 +243,19 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of knossos.wgl (oracle/lin_oracle.cpp, -O3 -march=native); JVM Knossos cannot run here",
     }
+    line["time_to_verdict_s"] = None
+    line["verdict"] = "unknown"
+    line["did_not_finish"] = ("the headline instance (tau_think 0) has 7.1e9 reachable configurations: knossos.wgl's cache would "
+                              "need > 100 GB and ~1 h at the sampled rate; only the bounded sample above is timed")
     if not args.no_full_run:
+        hv = workload(1, args, think_ms=args.v2v_think_ms)
         t = time.perf_counter()
-        r = oracle.check_linearizable(parts[0], m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_full_configs)
+        r = oracle.check_linearizable(hv, m, oracle.ALGO_WGL_COMPACT, max_configs=args.ref_full_configs)
         dt = time.perf_counter() - t
-        line["time_to_verdict_s"] = dt
-        line["verdict"] = {0: "valid", 1: "unknown", 2: "invalid"}[r["valid"]]
-        line["configs_to_verdict"] = r["configs"]
-        line["time_to_verdict_note"] = "ONE full run of key 1 to its verdict, single thread, outside the timed steps"
+        line["verdict_to_verdict"] = {
+            "workload": v2v_workload_name(args), "time_to_verdict_s": dt,
+            "verdict": {0: "valid", 1: "unknown", 2: "invalid"}[r["valid"]], "configs_to_verdict": r["configs"],
+            "note": "ONE full run to the verdict, single thread (knossos.wgl is single-threaded), outside the timed steps"}
     if not args.no_sharded:
         line["sharded"] = run_sharded_reference(args, world)
     print(json.dumps(line))
@@ -253,7 +269,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ops", type=int, default=10000)
     ap.add_argument("--clients", type=int, default=32)
-    ap.add_argument("--think-ms", type=float, default=5.0)
+    ap.add_argument("--think-ms", type=float, default=0.0)
+    ap.add_argument("--v2v-think-ms", type=float, default=5.0, help="tau_think of the instance both arms run to the verdict")
     ap.add_argument("--invalid", action="store_true", help="one stale read: exhaustive search, verdict invalid")
     ap.add_argument("--ref-configs", type=int, default=3_000_000)
     ap.add_argument("--cpu-baseline-configs", type=int, default=10_000_000)
@@ -360,7 +377,9 @@ def main():
             "gpu_launches": int(launches_t),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
-                         "peak_source": peak_src, "kernel": "wgl_search_kernel<bank,KW=2>",
+                         "traffic_source": tr.get("source") if tr else None,
+                         "peak_source": peak_src, "kernel": last["stats"].get("engine_level") and "level_search_kernel<bank,KW=2,exact>"
+                         or "wgl_search_kernel<bank,KW=2>",
                          "algorithmic_bytes": "16 B x (probes + inserts) per launch (SURVEY 8(d))",
                          "random_probe_ceiling_GBps": tr.get("table_probe_algo_GBps") if tr else None},
             "clocks": clocks,
@@ -368,6 +387,14 @@ def main():
         line["per_rank_kernel_s_per_step"] = [x / args.steps for x in per_rank_kern]
         if sharded is not None:
             line["sharded"] = sharded
+        if world == 1 and not args.no_full_run:
+            hv = workload(1, args, think_ms=args.v2v_think_ms)
+            with native.Context(device=local_rank, eager_reads=args.eager_reads) as vctx:
+                vr = min((vctx.check_linearizable(hv, m) for _ in range(3)), key=lambda r: r["seconds_total"])
+            line["verdict_to_verdict"] = {
+                "workload": v2v_workload_name(args), "time_to_verdict_s": vr["seconds_total"], "kernel_s": vr["seconds_kernel"],
+                "verdict": {0: "valid", 1: "unknown", 2: "invalid"}[vr["valid"]], "configs_to_verdict": vr["configs"],
+                "note": "C-ABI call with host buffers, best of 3"}
         if world == 1 and not args.eager_reads:
             with native.Context(device=local_rank, eager_reads=True) as ectx:
                 for _ in range(2):
@@ -375,7 +402,7 @@ def main():
                 line["product_default_eager_reads"] = {
                     "time_to_verdict_s": er["seconds_total"], "kernel_s": er["seconds_kernel"], "configs": er["configs"],
                     "verdict": {0: "valid", 1: "unknown", 2: "invalid"}[er["valid"]],
-                    "note": "same verdict from ~18x fewer configurations; not used for `value`/`e2e`"}
+                    "note": "same verdict from ~20x fewer configurations; not used for `value`/`e2e`"}
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()

@@ -307,6 +307,13 @@ int jtb_multi_check_set_full(jtb_multi* mg, const jtb_history* h, int linearizab
  * out[15..18] = scout steps, scout configs, shards decided by a scout, scouts launched */
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n);
 
+/* Page-locked host memory for the flattened arrays (what a JNI shim wraps in a direct ByteBuffer, what the Python
+ * mirror backs its numpy arrays with).  Not required: any host pointer works; page-locked ones are copied by DMA at the
+ * PCIe rate instead of being staged through the driver (the id lists of 100k-op set-full histories are ~600 MB).
+ * NULL when the allocation fails. */
+void* jtb_host_alloc(size_t bytes);
+void  jtb_host_free(void* p);
+
 /* ---- diagnostics: host preparation only (pairing, slots, tables) — no device work; returns seconds
  * or a negative value on malformed input.  Lets callers see the host share of time-to-verdict. */
 double jtb_prepare_seconds(const jtb_history* h, const jtb_model* m);

@@ -36,6 +36,7 @@ struct jtb_ctx {
     // cached device buffers (grown on demand, reused across calls)
     DevBuf table, pool, rows, classes, cls_inv, ctrl, found, maxrank;
     DevBuf sc_init, sc_tables, sc_stacks, sc_ctl;   // scouts: initial entries, private tables, stacks, control words
+    SfBuffers sf;                        // set-full pass: its device buffers
     DevBuf lv_ctrl, lv_buf[2];          // level engine: control block, the two level arrays
     size_t table_dirty = ~(size_t)0;    // bytes at the start of `table` that may hold old slots (level engine clears only these)
     int last_engine = 0;                // 0 work-list (visited table complete), 1 level (visited set is ephemeral)
@@ -154,6 +155,7 @@ int launch_level(jtb_ctx* ctx, const LvParams& p, int neg_ok, bool eager, int* g
     per_sm = std::min(per_sm, JTB_LV_CTAS);
     if (getenv("JTB_LV_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("JTB_LV_CTAS_PER_SM"))));
     const int grid = ctx->opts.search_ctas ? std::min<int>((int)ctx->opts.search_ctas, ctx->n_sms * per_sm) : ctx->n_sms * per_sm;
+    if (grid > 1024) { ctx->err = "level engine: more CTAs than barrier release words"; return -1; }
     *grid_out = grid;
     LvParams pp = p;
     int nk = neg_ok;
@@ -231,6 +233,8 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
     std::memset(&p.init, 0, sizeof p.init);
     p.init.n_in = searchable.size();
     p.init.epoch = 1;
+    p.init.s_in = 0; p.init.s_out = 1; p.init.s_spare = 2;
+    p.init.contig = 1;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     int attempts = 0, grid = 0;
     unsigned long long max_window = 0, max_width = 0, narrow_levels = 0, max_probe = 0;
@@ -243,6 +247,7 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         p.buf[0] = (uint64_t*)ctx->lv_buf[0].p;
         p.buf[1] = (uint64_t*)ctx->lv_buf[1].p;
         p.buf_cap = buf_cap;
+        p.seg_cap = buf_cap / LV_NSEG;
         p.init.zeroed = table_slots;
         if (ctx->opts.time_budget_ms) {   // what is left of the budget for this launch
             const double left = ctx->opts.time_budget_ms * 1e-3 - (now_s() - t_begin);
@@ -255,6 +260,22 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         if (rc) return rc;
         CK(cudaMemcpyAsync(&lc, ctx->lv_ctrl.p, sizeof lc, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (lc.abort) { ctx->err = "level engine: a grid barrier timed out (internal error)"; return -1; }
+#ifdef JTB_LV_PROF
+        {
+            const double wide = (double)std::max<unsigned long long>(lc.prof[9], 1), att = (double)std::max<unsigned long long>(lc.prof[8], 1);
+            fprintf(stderr, "[lv prof] attempts %llu (wide %llu)  per attempt, cycles: phase1 %.0f phase2 %.0f flush %.0f | per wide level: "
+                    "attempt %.0f barrier %.0f collect %.0f\n", lc.prof[8], lc.prof[9], lc.prof[0] / att, lc.prof[1] / att, lc.prof[2] / att,
+                    lc.prof[3] / wide, lc.prof[4] / wide, lc.prof[5] / wide);
+            unsigned long long bmin = ~0ull, bmax = 0, bsum = 0, wmin = ~0ull, wmax = 0, wsum = 0;
+            for (int i = 0; i < grid; ++i) {
+                bmin = std::min(bmin, lc.prof_cta[i][0]); bmax = std::max(bmax, lc.prof_cta[i][0]); bsum += lc.prof_cta[i][0];
+                wmin = std::min(wmin, lc.prof_cta[i][1]); wmax = std::max(wmax, lc.prof_cta[i][1]); wsum += lc.prof_cta[i][1];
+            }
+            fprintf(stderr, "[lv prof] per CTA over the launch, Mcycles: busy min %.1f avg %.1f max %.1f | barrier wait min %.1f avg %.1f max %.1f\n",
+                    bmin * 1e-6, bsum * 1e-6 / grid, bmax * 1e-6, wmin * 1e-6, wsum * 1e-6 / grid, wmax * 1e-6);
+        }
+#endif
         probes += lc.probes;
         max_window = std::max(max_window, lc.max_window);
         max_width = std::max(max_width, lc.max_width);
@@ -275,7 +296,20 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         if (ctx->table.p) { CK(cudaFree(ctx->table.p)); ctx->table = DevBuf(); }
         DevBuf grown;
         if (ensure(ctx, grown, new_buf)) return -1;
-        CK(cudaMemcpyAsync(grown.p, ctx->lv_buf[ii].p, (size_t)lc.fin.n_in * EW * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (lc.fin.contig) {
+            CK(cudaMemcpyAsync(grown.p, ctx->lv_buf[ii].p, (size_t)lc.fin.n_in * EW * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {   // gather the segments of the unfinished level into one contiguous run
+            size_t off = 0;
+            const size_t seg_cap = buf_cap / LV_NSEG;
+            for (int sg = 0; sg < LV_NSEG; ++sg) {
+                const size_t n = (size_t)lc.seg[lc.fin.s_in][sg].n;
+                if (!n) continue;
+                CK(cudaMemcpyAsync((char*)grown.p + off * EW * 8, (const char*)ctx->lv_buf[ii].p + (size_t)sg * seg_cap * EW * 8,
+                                   n * EW * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                off += n;
+            }
+            if (off != lc.fin.n_in) { ctx->err = "level engine: segment counts do not add up"; return -1; }
+        }
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaFree(ctx->lv_buf[ii].p));
         ctx->lv_buf[ii] = grown;
@@ -288,6 +322,7 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         // resume at the level that did not fit
         LvState r = lc.fin;
         r.stop = 0; r.cause = 0; r.boost = 0; r.attempt = 0; r.epoch = 1;
+        r.s_in = 0; r.s_out = 1; r.s_spare = 2; r.contig = 1;
         p.init = r;
         const int undecided = lc.n_undecided;
         std::memset(&lc, 0, sizeof lc);
@@ -445,6 +480,7 @@ void jtb_destroy(jtb_ctx* ctx) {
                       &ctx->lv_buf[0], &ctx->lv_buf[1]};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
+    ctx->sf.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_setup) cudaEventDestroy(ctx->ev_setup);
@@ -523,6 +559,7 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         if (ctx->opts.flags & JTB_OPT_ENGINE_WORKLIST) use_level = false;
         if (const char* en = getenv("JTB_ENGINE")) use_level = std::strcmp(en, "level") == 0;
         if (force_engine) use_level = force_engine == 1;
+        if (getenv("JTB_SCOUT_ONLY")) use_level = false;                     // test hook of the work-list engine
         if (P.n_ranks >= LV_MAX_RANKS || P.max_nc > 64) use_level = false;   // epoch tag bits / class mask width
         ctx->stats[19] = 0;
         if (use_level) {
@@ -982,7 +1019,7 @@ int jtb_check_set_full(jtb_ctx* ctx, const jtb_history* h, int linearizable, jtb
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
     ctx->fc.valid = false;
-    return run_set_full(ctx->stream, ctx->ev0, ctx->ev1, h, linearizable, out, ctx->err);
+    return run_set_full(ctx->stream, ctx->ev0, ctx->ev1, ctx->sf, h, linearizable, out, ctx->err, ctx->stats);
 }
 
 int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* accounts, int64_t total_amount,
@@ -992,6 +1029,18 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
     ctx->fc.valid = false;
     return run_bank_totals(ctx->stream, ctx->ev0, ctx->ev1, h, accounts, total_amount, out, ctx->err);
+}
+
+// Page-locked host memory for the caller's flattened arrays (the id lists of set-full reads are hundreds of MB: from
+// pageable memory the H2D copy is staged through the driver's bounce buffers at a fraction of the PCIe rate).
+void* jtb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void jtb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 double jtb_prepare_seconds(const jtb_history* h, const jtb_model* m) {

@@ -46,26 +46,36 @@ constexpr int LV_MAX_PROBE = 128;
 constexpr uint64_t LV_TAG_MASK = 0x3full << 56;
 constexpr int64_t LV_MAX_RANKS = 1ll << 24;
 
-struct LvSlot {   // what one attempt (a level, or its repetition with a larger window) produced; three in rotation
-    alignas(128) unsigned long long cnt;   // entries appended to the next level
-    int stop;      // 1: every shard is decided   2: give up (cause)
-    int cause;
-    int retry;     // a probe sequence ran off the window: repeat the level with a larger one
-    int pad;
+constexpr int LV_NSEG = 64;         // output segments of a level array (one append counter each: no hot atomic)
+constexpr unsigned LV_F_DECIDED = 1, LV_F_GIVEUP = 2, LV_F_RETRY = 4;   // result flags of an attempt (cause: bits 8..)
+
+struct LvSeg {
+    alignas(128) unsigned long long n;   // entries appended to this segment of the next level
 };
 struct LvState {   // identical in every thread of the grid
     unsigned long long level, attempt, n_in, total;
     int epoch, in_idx, boost, stop, cause;
+    int s_in, s_out, s_spare;    // roles of the three counter sets: input counts / this attempt's output / being reset
+    int contig;                  // the input is still the launch's contiguous run (not segmented)
     unsigned long long zeroed;   // table slots known to be initialised
+};
+struct LvRelease {
+    alignas(32) unsigned long long gen;
 };
 struct LvCtrl {
     alignas(128) unsigned long long bar;     // grid barrier: arrivals, monotone
-    alignas(128) LvSlot slot[3];
+    alignas(128) LvSeg seg[3][LV_NSEG];      // append counters, three sets in rotation (input / output / spare)
+    alignas(128) unsigned flags[3][32];      // result flags of the attempt whose output set is [i] (word 0 used)
     alignas(128) LvState pub;                // state after a run of narrow levels (CTA 0 -> everyone)
     alignas(128) int n_undecided;
+    int abort;                               // a grid barrier timed out (internal error)
     alignas(128) unsigned long long probes;
     unsigned long long max_probe_len, max_width, max_window, narrow_levels, retries, t0, t1;
     LvState fin;
+    // -DJTB_LV_PROF builds only: cycle sums of CTA 0 / warp 0 per section, and per-CTA busy / wait cycles at barriers
+    unsigned long long prof[16];
+    unsigned long long prof_cta[1024][2];
+    alignas(128) LvRelease release[1024];    // grid barrier: one release word per CTA (no shared polling line)
 };
 
 struct LvParams {
@@ -76,6 +86,7 @@ struct LvParams {
     uint64_t table_slots;     // capacity (power of two)
     uint64_t* buf[2];         // level arrays, entries of EW words
     uint64_t buf_cap;         // entries per array
+    uint64_t seg_cap;         // = buf_cap / LV_NSEG: entries per output segment
     LvCtrl* ctrl;
     int* shard_found;
     int* shard_max_rank;
@@ -156,19 +167,60 @@ __device__ __forceinline__ int lv_insert(uint64_t* table, uint64_t mask, const u
     return -1;
 }
 
-__device__ __forceinline__ void lv_grid_barrier(unsigned long long* bar, unsigned long long& target, bool patient) {
+// Grid barrier.  Arrival: one atomicAdd on a monotone counter.  Release: the LAST arriver writes one word per CTA, and
+// every CTA polls only its own word (444 pollers on one line delayed the arrivals themselves).  `gen` is kept by every
+// thread.  Returns false when the wait exceeds 20 s (900 s for the CTAs that sit out a run of narrow levels) — a lost CTA would
+// otherwise hang the device: the kernel then ends
+// with ctrl->abort set and the host reports an internal error.
+#ifdef JTB_LV_PROF
+#define LV_PROF(i, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_ = clock64(); ctrl->prof[i] += t_ - (t0); (t0) = t_; } } while (0)
+#else
+#define LV_PROF(i, t0) do { } while (0)
+#endif
+
+__device__ __forceinline__ bool lv_grid_barrier(LvCtrl* ctrl, unsigned long long& gen, bool patient) {
+    __shared__ int s_last, s_ok;
+    gen++;
     __syncthreads();
+#ifdef JTB_LV_PROF
+    __shared__ long long s_t_leave;
+    long long t_arrive = 0;
     if (threadIdx.x == 0) {
-        target += gridDim.x;
+        t_arrive = clock64();
+        if (gen > 1) ctrl->prof_cta[blockIdx.x][0] += t_arrive - s_t_leave;
+    }
+#endif
+    if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(bar, 1ull);
-        unsigned ns = 20;
-        while (ld_volatile(bar) < target) {
-            if (patient) { __nanosleep(ns); if (ns < 400) ns += ns; }
-        }
-        __threadfence();
+        const unsigned long long old = atomicAdd(&ctrl->bar, 1ull);
+        s_last = old + 1 == gen * gridDim.x;
+        s_ok = 1;
     }
     __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) *(volatile unsigned long long*)&ctrl->release[i].gen = gen;
+    }
+    if (threadIdx.x == 0) {
+        unsigned ns = 20;
+        unsigned long long t_wait = 0;
+        unsigned spins = 0;
+        while (ld_volatile(&ctrl->release[blockIdx.x].gen) < gen) {
+            if (patient) { __nanosleep(ns); if (ns < 400) ns += ns; }
+            if ((++spins & 0xfff) == 0) {
+                const unsigned long long now = globaltimer();
+                if (!t_wait) t_wait = now;
+                if (now - t_wait > (patient ? 900000000000ull : 20000000000ull) || ld_volatile(&ctrl->abort)) { atomicExch(&ctrl->abort, 1); s_ok = 0; break; }
+            }
+        }
+        __threadfence();
+#ifdef JTB_LV_PROF
+        s_t_leave = clock64();
+        ctrl->prof_cta[blockIdx.x][1] += s_t_leave - t_arrive;
+#endif
+    }
+    __syncthreads();
+    return s_ok != 0;
 }
 
 __host__ __device__ inline uint64_t lv_window(const LvParams& p, unsigned long long n_in, int boost) {
@@ -180,24 +232,29 @@ __host__ __device__ inline uint64_t lv_window(const LvParams& p, unsigned long l
     return s < p.table_slots ? s : p.table_slots;
 }
 
-// state transition after an attempt — evaluated identically by every thread that needs it
-__device__ __forceinline__ void lv_advance(const LvParams& p, LvState& st, unsigned long long cnt, int stop, int cause, int retry) {
+// state transition after an attempt — evaluated identically by every thread that needs it.
+// cnt = entries appended (sum over the segments), over = some segment ran past its capacity.
+__device__ __forceinline__ void lv_advance(const LvParams& p, LvState& st, unsigned long long cnt, bool over, unsigned flags) {
     st.attempt++;
     st.epoch = (st.epoch + 1) & 63;
-    if (stop == 2) { st.stop = 2; st.cause = cause; return; }
-    if (retry) {
+    const int o_in = st.s_in, o_out = st.s_out, o_spare = st.s_spare;
+    if (flags & LV_F_GIVEUP) { st.stop = 2; st.cause = (int)(flags >> 8); return; }
+    if (flags & LV_F_RETRY) {
         if (lv_window(p, st.n_in, st.boost) >= p.table_slots) { st.stop = 2; st.cause = JTB_CAUSE_TABLE_FULL; return; }
         st.boost++;
-        return;   // same level, same input, larger window, new epoch
+        st.s_out = o_spare; st.s_spare = o_out;   // same level, same input, larger window, new epoch
+        return;
     }
+    if (over) { st.stop = 2; st.cause = JTB_CAUSE_TABLE_FULL; return; }
     st.total += cnt;
-    if (stop == 1) { st.stop = 1; return; }
+    if (flags & LV_F_DECIDED) { st.stop = 1; return; }
     if (cnt == 0) { st.stop = 1; return; }                        // exhausted: the undecided shards are INVALID
-    if (cnt > p.buf_cap) { st.stop = 2; st.cause = JTB_CAUSE_TABLE_FULL; return; }
     if (p.max_configs && st.total >= p.max_configs) { st.stop = 2; st.cause = JTB_CAUSE_BUDGET; return; }
     st.level++;
     st.n_in = cnt;
     st.in_idx ^= 1;
+    st.contig = 0;
+    st.s_in = o_out; st.s_out = o_spare; st.s_spare = o_in;
 }
 
 template <int MODEL, int KW, bool EAGER>
@@ -209,6 +266,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
     using Scratch = LvScratch<KW, EW, BAL>;
     extern __shared__ __align__(16) unsigned char lv_smem[];
     __shared__ LvState s_state;
+    __shared__ unsigned long long s_seg_start[LV_NSEG + 1];   // exclusive prefix of the input segments' counts
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
     Scratch& S = reinterpret_cast<Scratch*>(lv_smem)[warp];
@@ -217,19 +275,35 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
     T.rows = p.rows; T.classes = p.classes; T.cls_inv_pos = p.cls_inv_pos; T.row_words = p.row_words; T.sum_off = p.sum_off;
 
     LvState st = p.init;
-    unsigned long long bar_target = 0;
+    unsigned long long bar_gen = 0;
     unsigned long long my_probes = 0;
     int my_max_probe = 0;
-    int wit_shard = -1, wit_rank = -1;   // lane-private filter for the witness atomicMax
+    int wit_shard = -1, wit_rank = -1;   // warp-uniform filter for the witness atomicMax
     if (blockIdx.x == 0 && tid == 0) ctrl->t0 = globaltimer();
+    // the first input of a launch is ONE contiguous run at the start of the array
+    if (tid <= LV_NSEG) s_seg_start[tid] = tid == 0 ? 0 : st.n_in;
+    __syncthreads();
+
+    // Where the idx-th configuration of the level lives: segment by binary search in the prefix, then the offset.
+    auto entry_of = [&](const LvState& a, unsigned long long idx) -> const uint64_t* {
+        int lo = 0, hi = LV_NSEG;       // largest s with seg_start[s] <= idx
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_seg_start[mid] <= idx) lo = mid; else hi = mid;
+        }
+        // (a launch's first input is one contiguous run: prefix [0, n, n, ...] puts all of it in "segment 0" at offset 0)
+        return p.buf[a.in_idx] + ((unsigned long long)lo * p.seg_cap + (idx - s_seg_start[lo])) * EW;
+    };
 
     // ---- one level attempt over the chunks [first, first + stride, ...) of the input array -------------------
     // Chunk = G configurations for one warp (G = 1, 2, .. 32: the smallest that gives every participating warp at most
     // one chunk, so a narrow level is spread over all warps and each has few children = few probe rounds).
     auto run_attempt = [&](const LvState& a, unsigned first_chunk, unsigned chunk_stride) {
-        const uint64_t* in = p.buf[a.in_idx];
         uint64_t* out = p.buf[a.in_idx ^ 1];
-        LvSlot* res = &ctrl->slot[a.attempt % 3];
+        unsigned* res_flags = &ctrl->flags[a.s_out][0];
+        const unsigned my_seg = first_chunk % LV_NSEG;
+        unsigned long long* my_cnt = &ctrl->seg[a.s_out][my_seg].n;
+        uint64_t* my_out = out + (unsigned long long)my_seg * p.seg_cap * EW;
         const uint64_t wmask = lv_window(p, a.n_in, a.boost) - 1;
         const uint64_t tag = (uint64_t)a.epoch << 56;
         unsigned G = 32;
@@ -238,18 +312,22 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
         unsigned stg_head = 0, stg_tail = 0;   // warp-uniform
         auto flush = [&](unsigned n) {
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&res->cnt, (unsigned long long)n);
+            if (lane == 0) base = atomicAdd(my_cnt, (unsigned long long)n);
             base = __shfl_sync(FULL, base, 0);
-            if (base + n <= p.buf_cap) {
-                uint64_t* dst = out + base * EW;
+            if (base + n <= p.seg_cap) {
+                uint64_t* dst = my_out + base * EW;
                 for (unsigned x = lane; x < n * EW; x += 32) {
                     const unsigned e = x / EW, k = x - e * EW;
                     dst[x] = S.stage[(stg_head + e) % LV_STAGE][k];
                 }
-            }   // else: cnt > buf_cap is seen by everyone after the barrier (TABLE_FULL)
+            }   // else: the count beyond seg_cap is seen by everyone after the barrier (TABLE_FULL -> the host grows)
             stg_head += n;
             __syncwarp();
         };
+#ifdef JTB_LV_PROF
+        long long tp = clock64();
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->prof[8]++;
+#endif
         for (unsigned chunk = first_chunk; chunk < n_chunks; chunk += chunk_stride) {
             // ---------------- phase 1: lane = configuration ------------------------------------------------
             const unsigned long long idx = (unsigned long long)chunk * G + lane;
@@ -260,7 +338,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 X.todo = 0; X.rd_ok = 0; X.ncls = 0; X.cls_i = 0;
                 X.fr_pos = 0; X.shard = 0; X.gj_end = 0; X.cls_base = 0; X.rslot = 0;
                 if (have) {
-                    const uint64_t* e = in + idx * EW;
+                    const uint64_t* e = entry_of(a, idx);
 #pragma unroll
                     for (int i = 0; i < KW; ++i) X.w[i] = ldcg64(e + i);
                     if constexpr (BAL) {
@@ -307,6 +385,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 const unsigned v = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += v;
             }
+            LV_PROF(0, tp);   // phase 1
             S.start[lane] = incl - c;
             const unsigned total = __shfl_sync(FULL, incl, 31);
             if (lane == 0) S.start[32] = total;
@@ -318,6 +397,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 Child<KW> ch;
                 bool is_new = false;
                 int owner = 0;
+                int adv_shard = -1, adv_rank = -1;
                 if (act) {
                     int lo = 0, hi = 32;       // largest o with start[o] <= g
                     while (hi - lo > 1) {
@@ -349,22 +429,34 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                         if (ch.done) {
                             // every :ok op of the shard is linearized -> VALID
                             if (atomicExch(&p.shard_found[Y.shard], 1) == 0) {
-                                if (atomicSub(&ctrl->n_undecided, 1) == 1) atomicCAS(&res->stop, 0, 1);
+                                if (atomicSub(&ctrl->n_undecided, 1) == 1) atomicOr(res_flags, LV_F_DECIDED);
                             }
                         } else {
                             int plen;
                             const int r = lv_insert<KW>(p.table, wmask, ch.w, tag, &plen);
                             my_probes++;
                             my_max_probe = max(my_max_probe, plen);
-                            if (r < 0) atomicExch(&res->retry, 1);
+                            if (r < 0) atomicOr(res_flags, LV_F_RETRY);
                             is_new = r == 1;
                             if constexpr (BAL) {
                                 if (is_new && ch.d < 0) Y.load_transfer(t_slot, ch);   // only NEW children need the transfer
                             }
-                            if (is_new && ch.cgj > Y.gj && (wit_shard != Y.shard || wit_rank < ch.cgj)) {
-                                wit_shard = Y.shard; wit_rank = ch.cgj;
-                                atomicMax(&p.shard_max_rank[Y.shard], ch.cgj);
-                            }
+                            if (is_new && ch.cgj > Y.gj) { adv_shard = Y.shard; adv_rank = ch.cgj; }
+                        }
+                    }
+                }
+                // ---- witness bookkeeping: furthest frontier reached (one RED per warp and advance, not per lane) ----
+                {
+                    const int best = __reduce_max_sync(FULL, adv_rank);
+                    if (best >= 0) {
+                        const unsigned who = __ballot_sync(FULL, adv_rank == best);
+                        const int bshard = __shfl_sync(FULL, adv_shard, __ffs(who) - 1);
+                        const bool mixed = __any_sync(FULL, adv_rank >= 0 && adv_shard != bshard);
+                        if (mixed) {   // several shards in one round (multi-key histories): every lane for itself
+                            if (adv_rank >= 0) atomicMax(&p.shard_max_rank[adv_shard], adv_rank);
+                        } else if (wit_shard != bshard || wit_rank < best) {
+                            wit_shard = bshard; wit_rank = best;
+                            if (lane == 0) atomicMax(&p.shard_max_rank[bshard], best);
                         }
                     }
                 }
@@ -396,8 +488,44 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 }
             }
             __syncwarp();   // the scratch of this chunk is dead
+            LV_PROF(1, tp);   // phase 2
         }
         if (stg_tail != stg_head) flush(stg_tail - stg_head);
+        LV_PROF(2, tp);       // final flush
+    };
+
+    // After an attempt (and the barrier / __syncthreads behind it): ONE warp of the CTA reads the 64 segment counts and
+    // the flag word, builds the prefix the next attempt addresses its input with, and the new state.
+    auto collect = [&](LvState& a) {
+        if (warp == 0) {
+            const unsigned long long c0 = ld_volatile(&ctrl->seg[a.s_out][lane].n);
+            const unsigned long long c1 = ld_volatile(&ctrl->seg[a.s_out][lane + 32].n);
+            unsigned fl = 0;
+            if (lane == 0) fl = *(volatile unsigned*)&ctrl->flags[a.s_out][0];
+            const bool over = c0 > p.seg_cap || c1 > p.seg_cap;
+            unsigned long long i0 = c0, i1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v0 = __shfl_up_sync(FULL, i0, o), v1 = __shfl_up_sync(FULL, i1, o);
+                if (lane >= o) { i0 += v0; i1 += v1; }
+            }
+            const unsigned long long t0 = __shfl_sync(FULL, i0, 31);
+            const unsigned long long t1 = __shfl_sync(FULL, i1, 31);
+            const bool any_over = __any_sync(FULL, over);
+            LvState nx = a;
+            if (lane == 0) lv_advance(p, nx, t0 + t1, any_over, fl);
+            // the prefix belongs to the NEXT input = this output, unless the level is repeated (retry): then the old
+            // prefix stays (same input)
+            const bool repeated = (__shfl_sync(FULL, fl, 0) & LV_F_RETRY) != 0;
+            if (!repeated) {
+                s_seg_start[lane + 1] = i0;
+                s_seg_start[lane + 33] = t0 + i1;
+                if (lane == 0) s_seg_start[0] = 0;
+            }
+            if (lane == 0) s_state = nx;
+        }
+        __syncthreads();
+        a = s_state;
     };
 
     // ---- cooperative zero-fill of a grown window (the host cleared [0, zeroed_slots)) ---------------------------
@@ -406,6 +534,11 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
         const uint64_t n16 = (to - from) * KW / 2, off = from * KW / 2;
         for (uint64_t i = (uint64_t)blockIdx.x * LV_THREADS + tid; i < n16; i += (uint64_t)gridDim.x * LV_THREADS)
             t[off + i] = make_ulonglong2(0, 0);
+    };
+    auto reset_spare = [&](const LvState& a) {   // by ONE warp, during the attempt: the set nobody reads or writes now
+        ctrl->seg[a.s_spare][lane].n = 0;
+        ctrl->seg[a.s_spare][lane + 32].n = 0;
+        if (lane == 0) ctrl->flags[a.s_spare][0] = 0;
     };
 
     for (;;) {
@@ -416,65 +549,77 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
             if (win > st.zeroed) {
                 zero_fill(st.zeroed, win);
                 st.zeroed = win;
-                lv_grid_barrier(&ctrl->bar, bar_target, false);
+                if (!lv_grid_barrier(ctrl, bar_gen, false)) break;
             }
         }
         if (!narrow) {
-            if (blockIdx.x == 0 && tid == 0) {
-                LvSlot* nx = &ctrl->slot[(st.attempt + 1) % 3];   // idle during this attempt: reset for the next one
-                nx->cnt = 0; nx->stop = 0; nx->cause = 0; nx->retry = 0;
-                if (p.time_budget_ns && globaltimer() - ctrl->t0 > p.time_budget_ns) {
-                    LvSlot* res = &ctrl->slot[st.attempt % 3];
-                    res->cause = JTB_CAUSE_BUDGET;
-                    __threadfence();
-                    atomicExch(&res->stop, 2);
+            if (blockIdx.x == 0 && warp == LV_WARPS - 1) {
+                reset_spare(st);
+                if (lane == 0) {
+                    if (p.time_budget_ns && globaltimer() - ctrl->t0 > p.time_budget_ns)
+                        atomicOr(&ctrl->flags[st.s_out][0], LV_F_GIVEUP | ((unsigned)JTB_CAUSE_BUDGET << 8));
+                    if (st.n_in > ctrl->max_width) ctrl->max_width = st.n_in;
+                    const uint64_t win = lv_window(p, st.n_in, st.boost);
+                    if (win > ctrl->max_window) ctrl->max_window = win;
                 }
-                if (st.n_in > ctrl->max_width) ctrl->max_width = st.n_in;
-                const uint64_t win = lv_window(p, st.n_in, st.boost);
-                if (win > ctrl->max_window) ctrl->max_window = win;
             }
+#ifdef JTB_LV_PROF
+            long long tw = clock64();
+#endif
             run_attempt(st, (unsigned)warp * gridDim.x + blockIdx.x, (unsigned)gridDim.x * LV_WARPS);
-            lv_grid_barrier(&ctrl->bar, bar_target, false);
-            const LvSlot* res = &ctrl->slot[st.attempt % 3];
-            const unsigned long long cnt = ld_volatile(&res->cnt);
-            const int stop = ld_volatile(&res->stop), cause = ld_volatile(&res->cause), retry = ld_volatile(&res->retry);
-            lv_advance(p, st, cnt, stop, cause, retry);
-            // wide -> narrow: CTA 0 is about to recycle the result slots on its own; everyone must have read this one
-            if (!st.stop && st.n_in <= p.narrow_max) lv_grid_barrier(&ctrl->bar, bar_target, false);
+            LV_PROF(3, tw);   // whole attempt, CTA 0 thread 0's view
+            if (!lv_grid_barrier(ctrl, bar_gen, false)) break;
+            LV_PROF(4, tw);   // barrier
+            collect(st);
+            LV_PROF(5, tw);   // collect
+#ifdef JTB_LV_PROF
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->prof[9]++;
+#endif
+            // wide -> narrow: CTA 0 is about to recycle the counter sets on its own; everyone must have read this one
+            if (!st.stop && st.n_in <= p.narrow_max && !lv_grid_barrier(ctrl, bar_gen, false)) break;
         } else {
             if (blockIdx.x == 0) {
                 // CTA 0 runs narrow levels on its own until the search widens, stops or ends
                 for (;;) {
-                    if (tid == 0) {
-                        LvSlot* nx = &ctrl->slot[(st.attempt + 1) % 3];
-                        nx->cnt = 0; nx->stop = 0; nx->cause = 0; nx->retry = 0;
-                        if (p.time_budget_ns && (st.attempt & 63) == 0 && globaltimer() - ctrl->t0 > p.time_budget_ns) {
-                            LvSlot* res = &ctrl->slot[st.attempt % 3];
-                            res->cause = JTB_CAUSE_BUDGET;
-                            res->stop = 2;
+                    if (warp == LV_WARPS - 1) {
+                        reset_spare(st);
+                        if (lane == 0) {
+                            if (p.time_budget_ns && (st.attempt & 63) == 0 && globaltimer() - ctrl->t0 > p.time_budget_ns)
+                                atomicOr(&ctrl->flags[st.s_out][0], LV_F_GIVEUP | ((unsigned)JTB_CAUSE_BUDGET << 8));
+                            ctrl->narrow_levels++;
                         }
-                        ctrl->narrow_levels++;
                     }
                     run_attempt(st, (unsigned)warp, (unsigned)LV_WARPS);
                     __syncthreads();
-                    if (tid == 0) {
-                        const LvSlot* res = &ctrl->slot[st.attempt % 3];
-                        LvState nx = st;
-                        lv_advance(p, nx, ld_volatile(&res->cnt), ld_volatile(&res->stop), ld_volatile(&res->cause),
-                                   ld_volatile(&res->retry));
-                        s_state = nx;
-                    }
-                    __syncthreads();
-                    st = s_state;
+                    collect(st);
                     if (st.stop || st.n_in > p.narrow_max || lv_window(p, st.n_in, st.boost) > st.zeroed) break;
                 }
-                if (tid == 0) { ctrl->pub = st; __threadfence(); }
+                if (tid == 0) {
+                    ctrl->pub = st;
+                    __threadfence();
+                }
             }
-            lv_grid_barrier(&ctrl->bar, bar_target, blockIdx.x != 0);
+            if (!lv_grid_barrier(ctrl, bar_gen, blockIdx.x != 0)) break;
             if (blockIdx.x != 0) {
+                // the others pick the state up and rebuild the input prefix from the counter set that is now the input
                 if (tid == 0) lv_load_state(s_state, &ctrl->pub);
                 __syncthreads();
                 st = s_state;
+                if (warp == 0) {
+                    const unsigned long long c0 = ld_volatile(&ctrl->seg[st.s_in][lane].n);
+                    const unsigned long long c1 = ld_volatile(&ctrl->seg[st.s_in][lane + 32].n);
+                    unsigned long long i0 = c0, i1 = c1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned long long v0 = __shfl_up_sync(FULL, i0, o), v1 = __shfl_up_sync(FULL, i1, o);
+                        if (lane >= o) { i0 += v0; i1 += v1; }
+                    }
+                    const unsigned long long t0 = __shfl_sync(FULL, i0, 31);
+                    s_seg_start[lane + 1] = i0;
+                    s_seg_start[lane + 33] = t0 + i1;
+                    if (lane == 0) s_seg_start[0] = 0;
+                }
+                __syncthreads();
             }
         }
     }

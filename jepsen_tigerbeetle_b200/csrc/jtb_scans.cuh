@@ -29,12 +29,14 @@ namespace jtb {
 // =================================================================================================
 // set-full
 // =================================================================================================
-struct SfRead {        // one :ok read (device)
+struct SfRead {        // one :ok read (device), in completion (:ok index) order within its shard
     int32_t inv_idx, ok_idx;
     int64_t inv_time, ok_time;
     int64_t pl_off;    // into payload
     int32_t pl_len;
     int32_t shard;     // bit 31 set: :final? read
+    int32_t n_elig;    // elements of the shard tracked before this read completed: positions [0, n_elig)
+    int32_t pad;
 };
 constexpr int32_t SF_FINAL_BIT = (int32_t)0x80000000;
 struct SfShard {       // device
@@ -44,9 +46,13 @@ struct SfShard {       // device
     int64_t read_off;  // into reads
     int64_t bits_off;  // into bit matrix (uint32 words); row stride = words_per_row
     int32_t words_per_row;
+    int32_t id_min;    // direct id -> position table: lut[id - id_min] (lut_len > 0), else binary search
+    int64_t lut_off;
+    int32_t lut_len;
     int32_t pad;
+    int64_t sorted_off;  // (id, position) pairs sorted by id, for the binary search (lut_len == 0)
 };
-struct SfElem {        // device, sorted by id within a shard
+struct SfElem {        // device, by POSITION = order of the tracking :add :invoke within the shard
     int32_t id;
     int32_t add_inv_idx;   // last :add :invoke of this value
     int32_t add_ok_idx;    // first :add :ok after it, INT32_MAX if none
@@ -61,34 +67,53 @@ struct SfAcc {         // per element accumulators (device)
     int pad;
 };
 
+__device__ __forceinline__ int sf_position(const SfShard& sd, const int32_t* __restrict__ lut,
+                                           const int2* __restrict__ sorted, int32_t id) {
+    if (sd.lut_len > 0) {
+        const int64_t k = (int64_t)id - sd.id_min;
+        return (k >= 0 && k < sd.lut_len) ? __ldg(lut + sd.lut_off + k) : -1;
+    }
+    const int2* tb = sorted + sd.sorted_off;
+    int lo = 0, hi = sd.n_elems - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int2 v = __ldg(tb + mid);
+        if (v.x == id) return v.y;
+        if (v.x < id) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+__global__ void sf_init_acc(SfAcc* __restrict__ acc, int64_t n) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < n) acc[g] = SfAcc{0, 0, ~0ull, 0, 0};
+}
+
+// Stage A: the read-major bit-matrix P[r][position] from the id lists.  One warp per read.
+// read_flag bit 0: some tracked id occurs twice; bit 1: the read holds ids that were never :add-invoked in this key.
 __global__ void sf_build_bits(const SfRead* __restrict__ reads, int64_t n_reads, const SfShard* __restrict__ shards,
-                              const SfElem* __restrict__ elems, const int32_t* __restrict__ payload,
-                              uint32_t* __restrict__ bits, int* __restrict__ read_dup_flag) {
-    // one warp per read; lanes stride over the read's id list
+                              const int32_t* __restrict__ lut, const int2* __restrict__ sorted,
+                              const int32_t* __restrict__ payload, uint32_t* __restrict__ bits, int* __restrict__ read_flag) {
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_reads) return;
     const SfRead rd = reads[r];
     const SfShard sd = shards[rd.shard & ~SF_FINAL_BIT];
-    const SfElem* el = elems + sd.elem_off;
     uint32_t* rowbits = bits + sd.bits_off + (r - sd.read_off) * (int64_t)sd.words_per_row;
-    bool dup = false;
+    int fl = 0;
     for (int i = lane; i < rd.pl_len; i += 32) {
         const int32_t id = __ldg(payload + rd.pl_off + i);
-        int lo = 0, hi = sd.n_elems - 1, pos = -1;
-        while (lo <= hi) {
-            const int mid = (lo + hi) >> 1;
-            const int32_t v = __ldg(&el[mid].id);
-            if (v == id) { pos = mid; break; }
-            if (v < id) lo = mid + 1; else hi = mid - 1;
-        }
+        const int pos = sf_position(sd, lut, sorted, id);
         if (pos >= 0) {
             const uint32_t bit = 1u << (pos & 31);
             const uint32_t old = atomicOr(rowbits + (pos >> 5), bit);
-            dup |= (old & bit) != 0;
+            fl |= (old & bit) ? 1 : 0;
+        } else {
+            fl |= 2;
         }
     }
-    if (__any_sync(0xffffffffu, dup) && lane == 0) read_dup_flag[r] = 1;
+    fl = __reduce_or_sync(0xffffffffu, fl);
+    if (fl && lane == 0) read_flag[r] = fl;
 }
 
 // (read-all-invoked-adds) workloads/set_full.clj:51-75 on the same bit-matrix: a :final? :ok read is suspect
@@ -113,80 +138,90 @@ __global__ void sf_final_missing(const SfRead* __restrict__ reads, int64_t n_rea
     if (lane == 0) missing[r] = zeros;
 }
 
-// exact multiplicities for the (rare) reads that contain a repeated element
+// exact multiplicities for the (rare) reads that contain a repeated tracked element
 __global__ void sf_count_dups(const SfRead* __restrict__ reads, const int* __restrict__ flagged, int n_flagged,
-                              const SfShard* __restrict__ shards, const SfElem* __restrict__ elems,
-                              const int32_t* __restrict__ payload, SfAcc* __restrict__ acc) {
+                              const SfShard* __restrict__ shards, const int32_t* __restrict__ lut,
+                              const int2* __restrict__ sorted, const int32_t* __restrict__ payload, SfAcc* __restrict__ acc) {
+    if ((int)blockIdx.x >= n_flagged) return;
     const int r = flagged[blockIdx.x];
-    if (blockIdx.x >= n_flagged) return;
     const SfRead rd = reads[r];
     const SfShard sd = shards[rd.shard & ~SF_FINAL_BIT];
-    const SfElem* el = elems + sd.elem_off;
     for (int i = threadIdx.x; i < rd.pl_len; i += blockDim.x) {
         const int32_t id = payload[rd.pl_off + i];
         int cnt = 0;
         for (int j = 0; j < rd.pl_len; ++j) cnt += payload[rd.pl_off + j] == id;
         if (cnt > 1) {
-            int lo = 0, hi = sd.n_elems - 1;
-            while (lo <= hi) {
-                const int mid = (lo + hi) >> 1;
-                if (el[mid].id == id) { atomicMax(&acc[sd.elem_off + mid].dup_max, cnt); break; }
-                if (el[mid].id < id) lo = mid + 1; else hi = mid - 1;
-            }
+            const int pos = sf_position(sd, lut, sorted, id);
+            if (pos >= 0) atomicMax(&acc[sd.elem_off + pos].dup_max, cnt);
         }
     }
 }
 
-constexpr int SF_RCHUNK = 2048;  // reads per block in the column scan
+constexpr int SF_RCHUNK = 512;   // reads per thread-chunk of the column scan
 
-// grid: (element tiles of 256, read chunks, shards)
-__global__ void __launch_bounds__(256) sf_column_scan(const SfRead* __restrict__ reads, const SfShard* __restrict__ shards,
-                                                      const SfElem* __restrict__ elems, const uint32_t* __restrict__ bits,
-                                                      SfAcc* __restrict__ acc) {
+// Stage B, bit-parallel: one thread owns one 32-element WORD of the matrix for a chunk of reads.  Elements sit in the
+// order of their tracking :add :invoke, so "read r may constrain element e" (ok_idx[r] > add_inv[e]) is a PREFIX of
+// the positions: n_elig[r].  Pass 1 walks the chunk's reads in DESCENDING invocation order (order_desc): the first
+// eligible read that shows a bit set / clear is that element's last_present / last_absent inside the chunk (chunks
+// merge by atomicMax); pass 2 walks them in completion order: the first eligible present read is known_read (atomicMin).
+// A word stops as soon as all of its 32 elements are settled.
+// grid: (word tiles of 128, read chunks, shards)
+__global__ void __launch_bounds__(128) sf_column_scan(const SfRead* __restrict__ reads, const SfShard* __restrict__ shards,
+                                                      const int32_t* __restrict__ order_desc,
+                                                      const uint32_t* __restrict__ bits, SfAcc* __restrict__ acc) {
     const SfShard sd = shards[blockIdx.z];
-    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int w = blockIdx.x * 128 + threadIdx.x;
     const int r0 = blockIdx.y * SF_RCHUNK;
-    if (blockIdx.x * 256 >= sd.n_elems || r0 >= sd.n_reads) return;
+    if (blockIdx.x * 128 >= sd.words_per_row || r0 >= sd.n_reads) return;
     const int r1 = min(sd.n_reads, r0 + SF_RCHUNK);
-    __shared__ int s_inv[256], s_ok[256];
-    const bool live = e < sd.n_elems;
-    const int add_inv = live ? elems[sd.elem_off + e].add_inv_idx : 0x7fffffff;
-    unsigned long long lp = 0, la = 0, kn = ~0ull;
-    const uint32_t* col = bits + sd.bits_off + (e >> 5);
-    for (int rb = r0; rb < r1; rb += 256) {
-        __syncthreads();
-        if (rb + threadIdx.x < r1) {
-            s_inv[threadIdx.x] = reads[sd.read_off + rb + threadIdx.x].inv_idx;
-            s_ok[threadIdx.x] = reads[sd.read_off + rb + threadIdx.x].ok_idx;
-        }
-        __syncthreads();
-        const int n = min(256, r1 - rb);
-        if (live) {
-#pragma unroll 4
-            for (int k = 0; k < n; ++k) {
-                const int r = rb + k;
-                const uint32_t wv = __ldg(col + (int64_t)r * sd.words_per_row);
-                if (s_ok[k] > add_inv) {
-                    const bool present = (wv >> (e & 31)) & 1u;
-                    const unsigned long long iv = ((unsigned long long)(uint32_t)(s_inv[k] + 1) << 32) | (uint32_t)r;
-                    if (present) {
-                        lp = max(lp, iv);
-                        kn = min(kn, ((unsigned long long)(uint32_t)s_ok[k] << 32) | (uint32_t)r);
-                    } else {
-                        la = max(la, iv);
-                    }
-                }
-            }
+    __shared__ int s_r[SF_RCHUNK], s_inv[SF_RCHUNK], s_elig[SF_RCHUNK];
+    const bool live = w < sd.words_per_row;
+    const int valid_bits = live ? min(32, sd.n_elems - w * 32) : 0;
+    const uint32_t all = valid_bits >= 32 ? 0xffffffffu : ((1u << valid_bits) - 1);
+    const uint32_t* col = bits + sd.bits_off + w;
+    SfAcc* a = acc + sd.elem_off + (int64_t)w * 32;
+    // ---- pass 1: descending invocation order -> last_present / last_absent ------------------------------------
+    for (int k = threadIdx.x; k < r1 - r0; k += 128) {
+        const int r = order_desc[sd.read_off + r0 + k];
+        s_r[k] = r;
+        s_inv[k] = reads[sd.read_off + r].inv_idx;
+        s_elig[k] = reads[sd.read_off + r].n_elig;
+    }
+    __syncthreads();
+    if (live) {
+        uint32_t need_p = all, need_a = all;
+        for (int k = 0; k < r1 - r0 && (need_p | need_a); ++k) {
+            const int e = s_elig[k] - w * 32;
+            if (e <= 0) continue;
+            const uint32_t el = e >= 32 ? 0xffffffffu : ((1u << e) - 1);
+            const int r = s_r[k];
+            const uint32_t wv = __ldg(col + (int64_t)r * sd.words_per_row);
+            uint32_t np = wv & el & need_p, na = ~wv & el & need_a;
+            need_p &= ~np; need_a &= ~na;
+            const unsigned long long iv = ((unsigned long long)(uint32_t)(s_inv[k] + 1) << 32) | (uint32_t)r;
+            while (np) { const int b = __ffs(np) - 1; np &= np - 1; atomicMax(&a[b].last_present, iv); }
+            while (na) { const int b = __ffs(na) - 1; na &= na - 1; atomicMax(&a[b].last_absent, iv); }
         }
     }
+    __syncthreads();
+    // ---- pass 2: completion order -> known_read ------------------------------------------------------------------
+    for (int k = threadIdx.x; k < r1 - r0; k += 128) {
+        s_inv[k] = reads[sd.read_off + r0 + k].ok_idx;
+        s_elig[k] = reads[sd.read_off + r0 + k].n_elig;
+    }
+    __syncthreads();
     if (live) {
-        SfAcc* a = &acc[sd.elem_off + e];
-        if (gridDim.y == 1) {
-            a->last_present = lp; a->last_absent = la; a->known_read = kn;
-        } else {
-            if (lp) atomicMax(&a->last_present, lp);
-            if (la) atomicMax(&a->last_absent, la);
-            if (kn != ~0ull) atomicMin(&a->known_read, kn);
+        uint32_t need_k = all;
+        for (int k = 0; k < r1 - r0 && need_k; ++k) {
+            const int e = s_elig[k] - w * 32;
+            if (e <= 0) continue;
+            const uint32_t el = e >= 32 ? 0xffffffffu : ((1u << e) - 1);
+            const int r = r0 + k;
+            const uint32_t wv = __ldg(col + (int64_t)r * sd.words_per_row);
+            uint32_t nk = wv & el & need_k;
+            need_k &= ~nk;
+            const unsigned long long kv = ((unsigned long long)(uint32_t)s_inv[k] << 32) | (uint32_t)r;
+            while (nk) { const int b = __ffs(nk) - 1; nk &= nk - 1; atomicMin(&a[b].known_read, kv); }
         }
     }
 }
@@ -250,24 +285,30 @@ __global__ void sf_classify(const SfRead* __restrict__ reads, const SfShard* __r
     out_id[o] = el.id;
 }
 
-#define SCK(call)                                                                  \
+// Device buffers of the set-full pass, cached in the context (grown on demand, reused across calls).
+struct SfBuffers {
+    struct Buf { void* p = nullptr; size_t cap = 0; } b[20];
+    void release() { for (auto& x : b) { if (x.p) cudaFree(x.p); x = Buf(); } }
+};
+
+#define SFK(call)                                                                  \
     do {                                                                           \
         cudaError_t e_ = (call);                                                   \
         if (e_ != cudaSuccess) {                                                   \
             err = std::string(#call) + ": " + cudaGetErrorString(e_);              \
-            cleanup();                                                             \
             return -1;                                                             \
         }                                                                          \
     } while (0)
 
-inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const jtb_history* h, int linearizable,
-                        jtb_setfull_out* out, std::string& err) {
+inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, SfBuffers& B, const jtb_history* h,
+                        int linearizable, jtb_setfull_out* out, std::string& err, unsigned long long* stats) {
     const double t_start = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     const int n_shards = h->n_shards;
     // ---- host pass: tracked elements and :ok reads per shard (O(events)) -----------------------
     std::vector<SfShard> shards(n_shards);
     std::vector<SfElem> elems;
-    std::vector<int32_t> elem_shard;
+    std::vector<int32_t> elem_shard, lut, order_desc;
+    std::vector<int2> sorted;
     std::vector<SfRead> reads;
     int64_t bits_words = 0;
     for (int s = 0; s < n_shards; ++s) {
@@ -301,115 +342,196 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
                     r.pl_off = h->payload_off[e];
                     r.pl_len = std::max(0, (int)h->payload_len[e]);
                     r.shard = s | ((h->flags && (h->flags[e] & JTB_FLAG_FINAL)) ? SF_FINAL_BIT : 0);
+                    r.n_elig = 0; r.pad = 0;
                     reads.push_back(r);
                 }
             }
         }
-        // creation order is dense over the surviving elements
+        // creation order is dense over the surviving elements; positions follow the tracking :add :invoke
         std::vector<std::pair<int32_t, Tr>> v(tracked.begin(), tracked.end());
         std::sort(v.begin(), v.end(), [](auto& x, auto& y) { return x.second.order < y.second.order; });
         for (size_t i = 0; i < v.size(); ++i) v[i].second.order = (int32_t)i;
-        std::sort(v.begin(), v.end(), [](auto& x, auto& y) { return x.first < y.first; });
+        std::sort(v.begin(), v.end(), [](auto& x, auto& y) { return x.second.add_inv_idx < y.second.add_inv_idx; });
         SfShard& sd = shards[s];
+        std::memset(&sd, 0, sizeof sd);
         sd.elem_off = (int64_t)elems.size();
         sd.n_elems = (int32_t)v.size();
         sd.read_off = read_off;
         sd.n_reads = (int32_t)(reads.size() - read_off);
         sd.words_per_row = (sd.n_elems + 31) / 32;
         sd.bits_off = bits_words;
-        sd.pad = 0;
         bits_words += (int64_t)sd.words_per_row * sd.n_reads;
-        for (auto& kv : v) {
+        // id -> position: a direct table when the ids are dense (account ids are consecutive integers,
+        // workloads/set_full.clj:22-32), a sorted (id, position) table otherwise
+        int32_t id_min = 0x7fffffff, id_max = (int32_t)0x80000000;
+        for (auto& kv : v) { id_min = std::min(id_min, kv.first); id_max = std::max(id_max, kv.first); }
+        const int64_t span = v.empty() ? 0 : (int64_t)id_max - id_min + 1;
+        sd.id_min = v.empty() ? 0 : id_min;
+        sd.lut_off = (int64_t)lut.size();
+        sd.sorted_off = (int64_t)sorted.size();
+        if (!v.empty() && span <= 4 * (int64_t)v.size() + 1024) {
+            sd.lut_len = (int32_t)span;
+            lut.resize(lut.size() + (size_t)span, -1);
+            for (size_t i = 0; i < v.size(); ++i) lut[(size_t)sd.lut_off + (size_t)(v[i].first - id_min)] = (int32_t)i;
+        } else {
+            sd.lut_len = 0;
+            const size_t o = sorted.size();
+            for (size_t i = 0; i < v.size(); ++i) sorted.push_back(int2{v[i].first, (int)i});
+            std::sort(sorted.begin() + o, sorted.end(), [](const int2& x, const int2& y) { return x.x < y.x; });
+        }
+        std::vector<int32_t> inv_sorted(v.size());
+        for (size_t i = 0; i < v.size(); ++i) {
+            const auto& kv = v[i];
+            inv_sorted[i] = kv.second.add_inv_idx;
             elems.push_back(SfElem{kv.first, kv.second.add_inv_idx, kv.second.add_ok_idx, kv.second.order, kv.second.add_ok_time});
             elem_shard.push_back(s);
         }
+        // per read: how many elements were tracked before it completed; reads in descending invocation order
+        const size_t o_desc = order_desc.size();
+        for (int r = 0; r < sd.n_reads; ++r) {
+            SfRead& rd = reads[(size_t)read_off + r];
+            rd.n_elig = (int32_t)(std::lower_bound(inv_sorted.begin(), inv_sorted.end(), rd.ok_idx) - inv_sorted.begin());
+            order_desc.push_back(r);
+        }
+        std::sort(order_desc.begin() + o_desc, order_desc.end(), [&](int32_t x, int32_t y) {
+            return reads[(size_t)read_off + x].inv_idx > reads[(size_t)read_off + y].inv_idx;
+        });
     }
     const int64_t n_elems = (int64_t)elems.size(), n_reads = (int64_t)reads.size();
     if (out->elem_capacity > 0 && out->elem_capacity < n_elems) { err = "elem_capacity too small"; return -4; }
-    // ---- device buffers ---------------------------------------------------------------------------
-    SfShard* d_shards = nullptr; SfElem* d_elems = nullptr; int32_t* d_elem_shard = nullptr; SfRead* d_reads = nullptr;
-    int32_t* d_payload = nullptr; uint32_t* d_bits = nullptr; int* d_dupflag = nullptr; SfAcc* d_acc = nullptr;
-    uint8_t* d_outcome = nullptr; long long* d_lat = nullptr; int* d_dup = nullptr; int32_t* d_id = nullptr;
-    SfShardOut* d_tally = nullptr; int* d_flagged = nullptr; int* d_missing = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_shards); cudaFree(d_elems); cudaFree(d_elem_shard); cudaFree(d_reads); cudaFree(d_payload);
-        cudaFree(d_bits); cudaFree(d_dupflag); cudaFree(d_acc); cudaFree(d_outcome); cudaFree(d_lat); cudaFree(d_dup);
-        cudaFree(d_id); cudaFree(d_tally); cudaFree(d_flagged); cudaFree(d_missing);
+    // ---- device buffers (cached in the context) ----------------------------------------------------
+    int nb = 0;
+    auto dev = [&](size_t bytes) -> void* {
+        SfBuffers::Buf& x = B.b[nb++];
+        bytes = std::max<size_t>(bytes, 16);
+        if (bytes > x.cap) {
+            if (x.p) cudaFree(x.p);
+            x.p = nullptr; x.cap = 0;
+            if (cudaMalloc(&x.p, bytes + bytes / 8) != cudaSuccess) { x.p = nullptr; return nullptr; }
+            x.cap = bytes + bytes / 8;
+        }
+        return x.p;
     };
-    auto nz = [](size_t b) { return b ? b : (size_t)16; };
-    SCK(cudaMalloc(&d_shards, nz(n_shards * sizeof(SfShard))));
-    SCK(cudaMalloc(&d_elems, nz(n_elems * sizeof(SfElem))));
-    SCK(cudaMalloc(&d_elem_shard, nz(n_elems * 4)));
-    SCK(cudaMalloc(&d_reads, nz(n_reads * sizeof(SfRead))));
-    SCK(cudaMalloc(&d_payload, nz((size_t)h->n_payload * 4)));
-    SCK(cudaMalloc(&d_bits, nz((size_t)bits_words * 4)));
-    SCK(cudaMalloc(&d_dupflag, nz(n_reads * 4)));
-    SCK(cudaMalloc(&d_acc, nz(n_elems * sizeof(SfAcc))));
-    SCK(cudaMalloc(&d_outcome, nz(n_elems)));
-    SCK(cudaMalloc(&d_lat, nz(n_elems * 8)));
-    SCK(cudaMalloc(&d_dup, nz(n_elems * 4)));
-    SCK(cudaMalloc(&d_id, nz(n_elems * 4)));
-    SCK(cudaMalloc(&d_tally, nz(n_shards * sizeof(SfShardOut))));
-    SCK(cudaMalloc(&d_missing, nz(n_reads * 4)));
-    SCK(cudaMemsetAsync(d_missing, 0, nz(n_reads * 4), st));
-    SCK(cudaMemcpyAsync(d_shards, shards.data(), n_shards * sizeof(SfShard), cudaMemcpyHostToDevice, st));
-    SCK(cudaMemcpyAsync(d_elems, elems.data(), n_elems * sizeof(SfElem), cudaMemcpyHostToDevice, st));
-    SCK(cudaMemcpyAsync(d_elem_shard, elem_shard.data(), n_elems * 4, cudaMemcpyHostToDevice, st));
-    SCK(cudaMemcpyAsync(d_reads, reads.data(), n_reads * sizeof(SfRead), cudaMemcpyHostToDevice, st));
-    SCK(cudaMemcpyAsync(d_payload, h->payload, (size_t)h->n_payload * 4, cudaMemcpyHostToDevice, st));
-    SCK(cudaEventRecord(e0, st));
-    SCK(cudaMemsetAsync(d_bits, 0, nz((size_t)bits_words * 4), st));
-    SCK(cudaMemsetAsync(d_dupflag, 0, nz(n_reads * 4), st));
-    SCK(cudaMemsetAsync(d_tally, 0, nz(n_shards * sizeof(SfShardOut)), st));
-    {   // accumulators: last_present = last_absent = 0, known_read = ~0, dup_max = 0
-        std::vector<SfAcc> init((size_t)n_elems, SfAcc{0, 0, ~0ull, 0, 0});
-        SCK(cudaMemcpyAsync(d_acc, init.data(), n_elems * sizeof(SfAcc), cudaMemcpyHostToDevice, st));
-        SCK(cudaStreamSynchronize(st));  // `init` must outlive the copy
+    SfShard* d_shards = (SfShard*)dev(n_shards * sizeof(SfShard));
+    SfElem* d_elems = (SfElem*)dev(n_elems * sizeof(SfElem));
+    int32_t* d_elem_shard = (int32_t*)dev(n_elems * 4);
+    SfRead* d_reads = (SfRead*)dev(n_reads * sizeof(SfRead));
+    int32_t* d_payload = (int32_t*)dev((size_t)h->n_payload * 4);
+    uint32_t* d_bits = (uint32_t*)dev((size_t)bits_words * 4);
+    int* d_flag = (int*)dev(n_reads * 4);
+    SfAcc* d_acc = (SfAcc*)dev(n_elems * sizeof(SfAcc));
+    uint8_t* d_outcome = (uint8_t*)dev(n_elems);
+    long long* d_lat = (long long*)dev(n_elems * 8);
+    int* d_dup = (int*)dev(n_elems * 4);
+    int32_t* d_id = (int32_t*)dev(n_elems * 4);
+    SfShardOut* d_tally = (SfShardOut*)dev(n_shards * sizeof(SfShardOut));
+    int* d_missing = (int*)dev(n_reads * 4);
+    int32_t* d_lut = (int32_t*)dev(lut.size() * 4);
+    int2* d_sorted = (int2*)dev(sorted.size() * sizeof(int2));
+    int32_t* d_order = (int32_t*)dev(order_desc.size() * 4);
+    int* d_flagged = (int*)dev(n_reads * 4);
+    for (int i = 0; i < nb; ++i)
+        if (!B.b[i].p) { err = "set-full: out of device memory"; return -1; }
+    unsigned long long h2d = 0;
+    auto up = [&](void* d, const void* src, size_t bytes) -> cudaError_t {
+        h2d += bytes;
+        return bytes ? cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+    };
+    SFK(cudaMemsetAsync(d_missing, 0, std::max<size_t>(n_reads * 4, 16), st));
+    SFK(up(d_shards, shards.data(), n_shards * sizeof(SfShard)));
+    SFK(up(d_elems, elems.data(), n_elems * sizeof(SfElem)));
+    SFK(up(d_elem_shard, elem_shard.data(), n_elems * 4));
+    SFK(up(d_reads, reads.data(), n_reads * sizeof(SfRead)));
+    SFK(up(d_lut, lut.data(), lut.size() * 4));
+    SFK(up(d_sorted, sorted.data(), sorted.size() * sizeof(int2)));
+    SFK(up(d_order, order_desc.data(), order_desc.size() * 4));
+    // the id lists: a true DMA when the caller's buffer is page-locked (jtb_host_alloc / cudaHostRegister), staged
+    // through the driver's bounce buffer otherwise
+    SFK(up(d_payload, h->payload, (size_t)h->n_payload * 4));
+    SFK(cudaEventRecord(e0, st));
+    SFK(cudaMemsetAsync(d_bits, 0, std::max<size_t>((size_t)bits_words * 4, 16), st));
+    SFK(cudaMemsetAsync(d_flag, 0, std::max<size_t>(n_reads * 4, 16), st));
+    SFK(cudaMemsetAsync(d_tally, 0, std::max<size_t>(n_shards * sizeof(SfShardOut), 16), st));
+    int launches = 0;
+    std::vector<int> flag((size_t)n_reads, 0);
+    if (n_elems > 0) {
+        sf_init_acc<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(d_acc, n_elems);
+        SFK(cudaGetLastError());
+        ++launches;
     }
     if (n_reads > 0 && n_elems > 0) {
         const int64_t threads = n_reads * 32;
-        sf_build_bits<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_reads, n_reads, d_shards, d_elems, d_payload, d_bits, d_dupflag);
-        SCK(cudaGetLastError());
-        int max_e = 0, max_r = 0;
-        for (auto& sd : shards) { max_e = std::max(max_e, sd.n_elems); max_r = std::max(max_r, sd.n_reads); }
-        dim3 grid((max_e + 255) / 256, (max_r + SF_RCHUNK - 1) / SF_RCHUNK, n_shards);
-        sf_column_scan<<<grid, 256, 0, st>>>(d_reads, d_shards, d_elems, d_bits, d_acc);
-        SCK(cudaGetLastError());
+        sf_build_bits<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_reads, n_reads, d_shards, d_lut, d_sorted, d_payload, d_bits, d_flag);
+        SFK(cudaGetLastError());
+        int max_w = 0, max_r = 0;
+        for (auto& sd : shards) { max_w = std::max(max_w, sd.words_per_row); max_r = std::max(max_r, sd.n_reads); }
+        dim3 grid((max_w + 127) / 128, (max_r + SF_RCHUNK - 1) / SF_RCHUNK, n_shards);
+        sf_column_scan<<<grid, 128, 0, st>>>(d_reads, d_shards, d_order, d_bits, d_acc);
+        SFK(cudaGetLastError());
         sf_final_missing<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_reads, n_reads, d_shards, d_bits, d_missing);
-        SCK(cudaGetLastError());
+        SFK(cudaGetLastError());
+        launches += 3;
         // duplicates (rare): exact multiplicities for flagged reads
-        std::vector<int> flag((size_t)n_reads);
-        SCK(cudaMemcpyAsync(flag.data(), d_dupflag, n_reads * 4, cudaMemcpyDeviceToHost, st));
-        SCK(cudaStreamSynchronize(st));
+        SFK(cudaMemcpyAsync(flag.data(), d_flag, n_reads * 4, cudaMemcpyDeviceToHost, st));
+        SFK(cudaStreamSynchronize(st));
         std::vector<int> flagged;
-        for (int64_t r = 0; r < n_reads; ++r) if (flag[r]) flagged.push_back((int)r);
+        for (int64_t r = 0; r < n_reads; ++r) if (flag[r] & 1) flagged.push_back((int)r);
         if (!flagged.empty()) {
-            SCK(cudaMalloc(&d_flagged, flagged.size() * 4));
-            SCK(cudaMemcpyAsync(d_flagged, flagged.data(), flagged.size() * 4, cudaMemcpyHostToDevice, st));
-            sf_count_dups<<<(unsigned)flagged.size(), 128, 0, st>>>(d_reads, d_flagged, (int)flagged.size(), d_shards, d_elems, d_payload, d_acc);
-            SCK(cudaGetLastError());
+            SFK(cudaMemcpyAsync(d_flagged, flagged.data(), flagged.size() * 4, cudaMemcpyHostToDevice, st));
+            sf_count_dups<<<(unsigned)flagged.size(), 128, 0, st>>>(d_reads, d_flagged, (int)flagged.size(), d_shards, d_lut, d_sorted, d_payload, d_acc);
+            SFK(cudaGetLastError());
+            ++launches;
         }
     }
     if (n_elems > 0) {
         sf_classify<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(d_reads, d_shards, d_elems, d_acc, n_elems, d_elem_shard,
                                                                       d_outcome, d_lat, d_dup, d_id, d_tally);
-        SCK(cudaGetLastError());
+        SFK(cudaGetLastError());
+        ++launches;
     }
-    SCK(cudaEventRecord(e1, st));
+    SFK(cudaEventRecord(e1, st));
     std::vector<SfShardOut> tally(n_shards);
-    SCK(cudaMemcpyAsync(tally.data(), d_tally, n_shards * sizeof(SfShardOut), cudaMemcpyDeviceToHost, st));
+    SFK(cudaMemcpyAsync(tally.data(), d_tally, n_shards * sizeof(SfShardOut), cudaMemcpyDeviceToHost, st));
     if (out->elem_capacity > 0 && n_elems > 0) {
-        SCK(cudaMemcpyAsync(out->elem_outcome, d_outcome, n_elems, cudaMemcpyDeviceToHost, st));
-        SCK(cudaMemcpyAsync(out->elem_latency_ms, d_lat, n_elems * 8, cudaMemcpyDeviceToHost, st));
-        SCK(cudaMemcpyAsync(out->elem_dup_count, d_dup, n_elems * 4, cudaMemcpyDeviceToHost, st));
-        SCK(cudaMemcpyAsync(out->elem_id, d_id, n_elems * 4, cudaMemcpyDeviceToHost, st));
+        SFK(cudaMemcpyAsync(out->elem_outcome, d_outcome, n_elems, cudaMemcpyDeviceToHost, st));
+        SFK(cudaMemcpyAsync(out->elem_latency_ms, d_lat, n_elems * 8, cudaMemcpyDeviceToHost, st));
+        SFK(cudaMemcpyAsync(out->elem_dup_count, d_dup, n_elems * 4, cudaMemcpyDeviceToHost, st));
+        SFK(cudaMemcpyAsync(out->elem_id, d_id, n_elems * 4, cudaMemcpyDeviceToHost, st));
     }
-    SCK(cudaStreamSynchronize(st));
-    float ms = 0;
-    SCK(cudaEventElapsedTime(&ms, e0, e1));
-    // read-all-invoked-adds: suspects = final reads with missing elements; ids enumerated from their bit rows
     std::vector<int> h_missing((size_t)n_reads, 0);
-    if (n_reads > 0) SCK(cudaMemcpy(h_missing.data(), d_missing, n_reads * 4, cudaMemcpyDeviceToHost));
+    if (n_reads > 0) SFK(cudaMemcpyAsync(h_missing.data(), d_missing, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    SFK(cudaStreamSynchronize(st));
+    float ms = 0;
+    SFK(cudaEventElapsedTime(&ms, e0, e1));
+    // ids that were never :add-invoked in their key but occur twice in one read: jepsen counts (frequencies v) over
+    // every value of a read, so they are :duplicated too.  Such reads are flagged by stage A (never in a healthy
+    // history); their id lists are counted here.
+    std::vector<int> untracked_dups(n_shards, 0);
+    {
+        std::vector<std::unordered_map<int32_t, int>> seen(n_shards);
+        for (int64_t r = 0; r < n_reads; ++r) {
+            if (!(flag[r] & 2)) continue;
+            const int s = reads[r].shard & ~SF_FINAL_BIT;
+            const SfShard& sd = shards[s];
+            std::unordered_map<int32_t, int> cnt;
+            for (int i = 0; i < reads[r].pl_len; ++i) {
+                const int32_t id = h->payload[reads[r].pl_off + i];
+                bool is_tracked;
+                if (sd.lut_len > 0) {
+                    const int64_t k = (int64_t)id - sd.id_min;
+                    is_tracked = k >= 0 && k < sd.lut_len && lut[(size_t)sd.lut_off + (size_t)k] >= 0;
+                } else {
+                    auto b0 = sorted.begin() + sd.sorted_off, b1 = b0 + sd.n_elems;
+                    auto it = std::lower_bound(b0, b1, id, [](const int2& x, int32_t v) { return x.x < v; });
+                    is_tracked = it != b1 && it->x == id;
+                }
+                if (!is_tracked) cnt[id]++;
+            }
+            for (auto& kv : cnt)
+                if (kv.second > 1 && seen[s].emplace(kv.first, 1).second) untracked_dups[s]++;
+        }
+    }
+    // read-all-invoked-adds: suspects = final reads with missing elements; ids enumerated from their bit rows
     std::vector<int> suspect_per_shard(n_shards, 0);
     out->n_suspect = 0;
     out->raia_valid = JTB_VALID;
@@ -425,17 +547,18 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
             if (out->suspect_capacity > 0) {
                 if (out->n_suspect >= out->suspect_capacity || cursor + h_missing[r] > out->missing_capacity) {
                     err = "suspect/missing capacity too small";
-                    cleanup();
                     return -4;
                 }
                 const SfShard& sd = shards[s];
                 rowbits.resize(sd.words_per_row);
-                SCK(cudaMemcpy(rowbits.data(), d_bits + sd.bits_off + (r - sd.read_off) * (int64_t)sd.words_per_row,
+                SFK(cudaMemcpy(rowbits.data(), d_bits + sd.bits_off + (r - sd.read_off) * (int64_t)sd.words_per_row,
                                (size_t)sd.words_per_row * 4, cudaMemcpyDeviceToHost));
                 out->suspect_shard[out->n_suspect] = s;
                 out->suspect_index[out->n_suspect] = reads[r].ok_idx;
-                for (int e = 0; e < sd.n_elems; ++e)  // elems are sorted by id inside a shard
+                const int64_t first = cursor;
+                for (int e = 0; e < sd.n_elems; ++e)
                     if (!((rowbits[e >> 5] >> (e & 31)) & 1u)) out->missing_ids[cursor++] = elems[sd.elem_off + e].id;
+                std::sort(out->missing_ids + first, out->missing_ids + cursor);
                 out->suspect_missing_off[out->n_suspect + 1] = cursor;
             }
             out->n_suspect++;
@@ -450,7 +573,7 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
         r.suspect_final_reads = suspect_per_shard[s];
         r.attempt_count = shards[s].n_elems;
         r.stable_count = tally[s].stable; r.lost_count = tally[s].lost; r.never_read_count = tally[s].never_read;
-        r.stale_count = tally[s].stale; r.duplicated_count = tally[s].duplicated;
+        r.stale_count = tally[s].stale; r.duplicated_count = tally[s].duplicated + untracked_dups[s];
         r.stable_latency_max_ms = tally[s].stable_lat_max; r.lost_latency_max_ms = tally[s].lost_lat_max;
         int valid;
         if (r.lost_count > 0) valid = JTB_INVALID;
@@ -463,11 +586,27 @@ inline int run_set_full(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const j
         out->n_failures += valid != JTB_VALID;
         if (out->elem_capacity > 0) out->elem_off[s + 1] = shards[s].elem_off + shards[s].n_elems;
     }
-    cleanup();
     out->seconds_kernel = ms * 1e-3;
     out->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_start;
+    if (stats) {
+        stats[11] = (unsigned long long)(ms * 1e3);
+        stats[12] = h2d;
+        stats[13] = (unsigned long long)(n_shards * sizeof(SfShardOut) + n_reads * 8 + (out->elem_capacity > 0 ? n_elems * 17 : 0));
+        stats[14] = (unsigned long long)launches;
+    }
     return 0;
 }
+#undef SFK
+
+#define SCK(call)                                                                  \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);              \
+            cleanup();                                                             \
+            return -1;                                                             \
+        }                                                                          \
+    } while (0)
 
 // =================================================================================================
 // bank totals

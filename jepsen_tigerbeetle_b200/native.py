@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
            "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds", "jtb_prepare_info",
-           "jtb_final_configs", "jtb_gather_bench", "jtb_multi_create", "jtb_multi_create_error", "jtb_multi_destroy", "jtb_multi_n_gpus",
+           "jtb_final_configs", "jtb_gather_bench", "jtb_host_alloc", "jtb_host_free", "jtb_multi_create", "jtb_multi_create_error", "jtb_multi_destroy", "jtb_multi_n_gpus",
            "jtb_multi_last_error", "jtb_multi_check_linearizable", "jtb_multi_check_set_full"]
 
 _lib = None
@@ -295,3 +295,30 @@ def prepare_info(h: FlatHistory, model: CModel) -> dict:
 
 def device_count() -> int:
     return lib().jtb_device_count()
+
+
+def pinned_copy(a):
+    """A copy of numpy array `a` in page-locked host memory (jtb_host_alloc): H2D copies of it run at the PCIe rate.
+    The block is released when the returned array (and every view of it) is gone."""
+    import weakref
+
+    import numpy as np
+    L = lib()
+    L.jtb_host_alloc.restype = C.c_void_p
+    L.jtb_host_alloc.argtypes = [C.c_size_t]
+    L.jtb_host_free.argtypes = [C.c_void_p]
+    ptr = L.jtb_host_alloc(max(a.nbytes, 16))
+    if not ptr:
+        raise NativeError("jtb_host_alloc failed")
+    raw = (C.c_char * max(a.nbytes, 1)).from_address(ptr)
+    base = np.frombuffer(raw, dtype=a.dtype, count=a.size)      # every view of the result keeps `base` alive
+    weakref.finalize(base, L.jtb_host_free, C.c_void_p(ptr))
+    out = base.reshape(a.shape)
+    out[...] = a
+    return out
+
+
+def pin_history(h: FlatHistory) -> FlatHistory:
+    """The history with its payload (the read id lists: the bulk of a set-full history) in page-locked memory."""
+    import dataclasses
+    return dataclasses.replace(h, payload=pinned_copy(h.payload))

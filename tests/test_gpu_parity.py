@@ -151,6 +151,43 @@ def test_set_full_c1(gpu_ctx, oracle_mod):
             sf_equal(gpu_ctx.check_set_full(h, lin), oracle_mod.check_set_full(h, lin))
 
 
+SF_KATS = [
+    ("stable", "0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read #{1}", [0, 1, 2, 3]),
+    ("never-read", "0:inv add 1, 0:ok add 1", [0, 1]),
+    ("lost", "0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read #{1}, 1:inv read, 1:ok read #{}", [0, 1, 2, 3, 4, 5]),
+    ("stale", "0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read #{}, 1:inv read, 1:ok read #{1}", [0, 1, 2, 3, 12, 13]),
+    ("read-before-add-ok", "0:inv add 1, 1:inv read, 1:ok read #{1}, 0:ok add 1", [0, 1, 2, 3]),
+    ("info-add-seen", "0:inv add 1, 0:info add 1, 1:inv read, 1:ok read #{1}", [0, 1, 2, 3]),
+    ("tracked-duplicate", "0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read [1 1]", [0, 1, 2, 3]),
+    # an id that was never :add-invoked occurs twice in one read: jepsen counts (frequencies v) over every value
+    ("untracked-duplicate", "0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read [1 7 7]", [0, 1, 2, 3]),
+    ("untracked-single", "0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read #{1 7}", [0, 1, 2, 3]),
+    # sparse ids: the id -> position lookup falls back from the direct table to the sorted table
+    ("sparse-ids", "0:inv add 5, 0:ok add 5, 0:inv add 900000, 0:ok add 900000, 0:inv add 70000000, 0:ok add 70000000, "
+                   "1:inv read, 1:ok read #{5 70000000}, 1:inv read, 1:ok read #{5 900000 70000000}", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]),
+    ("re-added-element", "0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read #{1}, 0:inv add 1, 0:ok add 1, 1:inv read, 1:ok read #{}",
+     [0, 1, 2, 3, 4, 5, 6, 7]),
+]
+
+
+@pytest.mark.parametrize("name,text,times", SF_KATS, ids=[k[0] for k in SF_KATS])
+def test_set_full_kats(gpu_ctx, oracle_mod, name, text, times):
+    h = H.flatten_ops(kat.ops(text, [t * 1_000_000 for t in times]), "set")
+    for lin in (True, False):
+        sf_equal(gpu_ctx.check_set_full(h, lin), oracle_mod.check_set_full(h, lin))
+
+
+def test_set_full_pinned_payload_and_buffer_reuse(gpu_ctx, oracle_mod):
+    """Page-locked id lists (jtb_host_alloc) and the context's cached device buffers: a large history, then a small
+    one, then the large one again through the same context."""
+    from jepsen_tigerbeetle_b200 import native
+    big = native.pin_history(synth.config_c4(seed=3, n_keys=4, n_ops=12000))
+    small = synth.config_c1(seed=2)
+    ob, os_ = oracle_mod.check_set_full(big), oracle_mod.check_set_full(small)
+    for h, o in ((big, ob), (small, os_), (big, ob)):
+        sf_equal(gpu_ctx.check_set_full(h), o)
+
+
 def test_set_full_multi_key_with_info(gpu_ctx, oracle_mod):
     h = synth.config_c4(seed=2, n_keys=8, n_ops=8000)
     sf_equal(gpu_ctx.check_set_full(h), oracle_mod.check_set_full(h))
