@@ -112,8 +112,9 @@ typedef struct jtb_model {
  * configuration counts are unaffected.  Set this flag to run the exhaustive search alone. */
 #define JTB_OPT_NO_SCOUTS 2
 /* Engine choice for jtb_check_linearizable.  Default (neither bit): the level-synchronous engine (csrc/jtb_level.cuh:
- * breadth-first by depth, visited set local to a level, bounded memory) for histories without crashed (:info) ops,
- * the work-list engine (csrc/jtb_wgl.cuh: depth-first locally, persistent visited table, scouts) otherwise.
+ * breadth-first by depth, visited set local to a level, bounded memory) for histories without crashed (:info) ops
+ * that are searched in the Knossos-exact space or are wide (nearly every client always has an op in flight), the
+ * work-list engine (csrc/jtb_wgl.cuh: depth-first locally, persistent visited table, scouts) otherwise.
  * Verdict, witness and exhaustive configuration counts are identical; the bits force one engine. */
 #define JTB_OPT_ENGINE_LEVEL    4
 #define JTB_OPT_ENGINE_WORKLIST 8

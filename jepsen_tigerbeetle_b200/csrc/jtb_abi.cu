@@ -147,7 +147,11 @@ template <int MODEL, int KW>
 int launch_level(jtb_ctx* ctx, const LvParams& p, int neg_ok, bool eager, int* grid_out) {
     constexpr int EW = KW + (MODEL == JTB_MODEL_BANK ? 4 : 0);
     const size_t smem = sizeof(LvScratch<KW, EW, MODEL == JTB_MODEL_BANK>) * LV_WARPS;
-    const void* k = eager ? (const void*)level_search_kernel<MODEL, KW, true> : (const void*)level_search_kernel<MODEL, KW, false>;
+    const void* k;
+    if (MODEL == JTB_MODEL_BANK && !neg_ok)
+        k = eager ? (const void*)level_search_kernel<MODEL, KW, true, false> : (const void*)level_search_kernel<MODEL, KW, false, false>;
+    else
+        k = eager ? (const void*)level_search_kernel<MODEL, KW, true, true> : (const void*)level_search_kernel<MODEL, KW, false, true>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LV_THREADS, smem));
@@ -158,8 +162,7 @@ int launch_level(jtb_ctx* ctx, const LvParams& p, int neg_ok, bool eager, int* g
     if (grid > 1024) { ctx->err = "level engine: more CTAs than barrier release words"; return -1; }
     *grid_out = grid;
     LvParams pp = p;
-    int nk = neg_ok;
-    void* args[] = {&pp, &nk};
+    void* args[] = {&pp};
     CK(cudaLaunchCooperativeKernel(k, dim3(grid), dim3(LV_THREADS), args, smem, ctx->stream));
     return 0;
 }
@@ -235,6 +238,7 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
     p.init.epoch = 1;
     p.init.s_in = 0; p.init.s_out = 1; p.init.s_spare = 2;
     p.init.contig = 1;
+    p.init.win = 0;   // (set per launch below: needs the table size)
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     int attempts = 0, grid = 0;
     unsigned long long max_window = 0, max_width = 0, narrow_levels = 0, max_probe = 0;
@@ -249,6 +253,7 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         p.buf_cap = buf_cap;
         p.seg_cap = buf_cap / LV_NSEG;
         p.init.zeroed = table_slots;
+        p.init.win = lv_window(p, p.init.n_in, 0);
         if (ctx->opts.time_budget_ms) {   // what is left of the budget for this launch
             const double left = ctx->opts.time_budget_ms * 1e-3 - (now_s() - t_begin);
             p.time_budget_ns = (unsigned long long)(std::max(left, 1e-3) * 1e9);
@@ -554,7 +559,14 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
             ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
             return -1;
         // ---- engine: level-synchronous sweep (jtb_level.cuh) or work list (jtb_wgl.cuh / jtb_search.cuh) ----------
-        bool use_level = P.max_nc == 0;   // crashed ops: the depth-first work list + scouts find linearizations sooner
+        const bool eager_mode = !(ctx->opts.flags & JTB_OPT_NO_EAGER_READS);
+        // Default choice (measured, profiles/r2_engines.md): histories with crashed ops -> work list (its depth-first
+        // order + scouts find the linearization of a valid history long before a breadth-first sweep would);
+        // Knossos-exact space -> level engine (wide levels: 1.2-4 G configs/s against 0.9, bounded memory);
+        // eager reads (product default) -> the search is narrow unless ~every client always has an op in flight
+        // (mean open ops per frontier row >= 26 of 32): narrow searches are a chain of short levels, where the work
+        // list's ~7 us per dependent step beats a grid barrier per level (67 vs 99 ms on the 10k-op bank history).
+        bool use_level = P.max_nc == 0 && (!eager_mode || P.mean_open >= 26.0);
         if (ctx->opts.flags & JTB_OPT_ENGINE_LEVEL) use_level = true;
         if (ctx->opts.flags & JTB_OPT_ENGINE_WORKLIST) use_level = false;
         if (const char* en = getenv("JTB_ENGINE")) use_level = std::strcmp(en, "level") == 0;
@@ -578,7 +590,6 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         // CTA deque / grid.  Two interchangeable search kernels: "tpc" (one THREAD per configuration, jtb_search.cuh:
         // throughput) and "warp" (one WARP per configuration, jtb_wgl.cuh: every child of a configuration probed in
         // the same round trip).  Default tpc; env JTB_KERNEL=warp|tpc overrides (A/B measurements).
-        const bool eager_mode = !(ctx->opts.flags & JTB_OPT_NO_EAGER_READS);
         bool use_tpc = false;
         if (const char* kk = getenv("JTB_KERNEL")) use_tpc = std::strcmp(kk, "warp") != 0;
         const int cand_rounds = P.S_pad / 32, cls_rounds = (P.max_nc + 31) / 32;

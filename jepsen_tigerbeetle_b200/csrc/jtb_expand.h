@@ -152,15 +152,22 @@ struct Expander {
                 const int32_t* sum = row + T.sum_off;
                 const int32_t want = BANK ? (int32_t)balhash : reg;
                 uint64_t match = 0;
+                // 16 slots (four 16 B loads, independent) per step: enough loads in flight without a register blow-up
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int b = 0; b < 4; ++b) {
+                    if (!((fastm >> (16 * b)) & 0xffffull)) continue;
+                    uint32_t mm = 0;
 #pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                    if ((fastm >> (4 * g)) & 0xfull) {
-                        const I4 v = ld_i4(sum + 4 * g);
-                        uint32_t mm = (v.x == want) | ((v.y == want) << 1) | ((v.z == want) << 2) | ((v.w == want) << 3);
+                    for (int g = 0; g < 4; ++g) {
+                        const I4 v = ld_i4(sum + 16 * b + 4 * g);
+                        uint32_t m4 = (v.x == want) | ((v.y == want) << 1) | ((v.z == want) << 2) | ((v.w == want) << 3);
                         if constexpr (REG)
-                            mm |= (v.x == JTB_NIL) | ((v.y == JTB_NIL) << 1) | ((v.z == JTB_NIL) << 2) | ((v.w == JTB_NIL) << 3);
-                        match |= (uint64_t)mm << (4 * g);
+                            m4 |= (v.x == JTB_NIL) | ((v.y == JTB_NIL) << 1) | ((v.z == JTB_NIL) << 2) | ((v.w == JTB_NIL) << 3);
+                        mm |= m4 << (4 * g);
                     }
+                    match |= (uint64_t)mm << (16 * b);
                 }
                 match &= fastm;
                 if constexpr (REG && !EAGER) { rd_ok |= match; match = 0; }   // the summary is exact: nothing left to look at

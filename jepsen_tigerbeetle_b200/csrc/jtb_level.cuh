@@ -57,13 +57,13 @@ struct LvState {   // identical in every thread of the grid
     int epoch, in_idx, boost, stop, cause;
     int s_in, s_out, s_spare;    // roles of the three counter sets: input counts / this attempt's output / being reset
     int contig;                  // the input is still the launch's contiguous run (not segmented)
+    unsigned long long win;      // hash window (slots) of the attempt this state describes = lv_window(n_in, boost)
     unsigned long long zeroed;   // table slots known to be initialised
 };
 struct LvRelease {
     alignas(32) unsigned long long gen;
 };
 struct LvCtrl {
-    alignas(128) unsigned long long bar;     // grid barrier: arrivals, monotone
     alignas(128) LvSeg seg[3][LV_NSEG];      // append counters, three sets in rotation (input / output / spare)
     alignas(128) unsigned flags[3][32];      // result flags of the attempt whose output set is [i] (word 0 used)
     alignas(128) LvState pub;                // state after a run of narrow levels (CTA 0 -> everyone)
@@ -75,7 +75,8 @@ struct LvCtrl {
     // -DJTB_LV_PROF builds only: cycle sums of CTA 0 / warp 0 per section, and per-CTA busy / wait cycles at barriers
     unsigned long long prof[16];
     unsigned long long prof_cta[1024][2];
-    alignas(128) LvRelease release[1024];    // grid barrier: one release word per CTA (no shared polling line)
+    alignas(128) LvRelease arrive[1024];     // grid barrier: one arrival word per CTA, watched by CTA 0 ...
+    alignas(128) LvRelease release[1024];    // ... and one release word per CTA, written by CTA 0
 };
 
 struct LvParams {
@@ -167,11 +168,11 @@ __device__ __forceinline__ int lv_insert(uint64_t* table, uint64_t mask, const u
     return -1;
 }
 
-// Grid barrier.  Arrival: one atomicAdd on a monotone counter.  Release: the LAST arriver writes one word per CTA, and
-// every CTA polls only its own word (444 pollers on one line delayed the arrivals themselves).  `gen` is kept by every
-// thread.  Returns false when the wait exceeds 20 s (900 s for the CTAs that sit out a run of narrow levels) — a lost CTA would
-// otherwise hang the device: the kernel then ends
-// with ctrl->abort set and the host reports an internal error.
+// Grid barrier without atomics.  Every CTA publishes its generation in its own arrival word; the threads of CTA 0 each
+// watch a few arrival words, and once all have arrived write one release word per CTA; every other CTA polls only its
+// own release word.  `gen` is kept by every thread.  Returns false when the wait exceeds 20 s (900 s for the CTAs that
+// sit out a run of narrow levels) — a lost CTA would otherwise hang the device: the kernel then ends with ctrl->abort
+// set and the host reports an internal error.
 #ifdef JTB_LV_PROF
 #define LV_PROF(i, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_ = clock64(); ctrl->prof[i] += t_ - (t0); (t0) = t_; } } while (0)
 #else
@@ -179,8 +180,9 @@ __device__ __forceinline__ int lv_insert(uint64_t* table, uint64_t mask, const u
 #endif
 
 __device__ __forceinline__ bool lv_grid_barrier(LvCtrl* ctrl, unsigned long long& gen, bool patient) {
-    __shared__ int s_last, s_ok;
+    __shared__ int s_ok;
     gen++;
+    if (threadIdx.x == 0) s_ok = 1;
     __syncthreads();
 #ifdef JTB_LV_PROF
     __shared__ long long s_t_leave;
@@ -190,44 +192,55 @@ __device__ __forceinline__ bool lv_grid_barrier(LvCtrl* ctrl, unsigned long long
         if (gen > 1) ctrl->prof_cta[blockIdx.x][0] += t_arrive - s_t_leave;
     }
 #endif
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long old = atomicAdd(&ctrl->bar, 1ull);
-        s_last = old + 1 == gen * gridDim.x;
-        s_ok = 1;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) *(volatile unsigned long long*)&ctrl->release[i].gen = gen;
-    }
-    if (threadIdx.x == 0) {
-        unsigned ns = 20;
+    const unsigned long long limit = patient ? 900000000000ull : 20000000000ull;
+    auto wait_for = [&](const unsigned long long* word) {
+        unsigned ns = 20, spins = 0;
         unsigned long long t_wait = 0;
-        unsigned spins = 0;
-        while (ld_volatile(&ctrl->release[blockIdx.x].gen) < gen) {
+        while (ld_volatile(word) < gen) {
             if (patient) { __nanosleep(ns); if (ns < 400) ns += ns; }
             if ((++spins & 0xfff) == 0) {
                 const unsigned long long now = globaltimer();
                 if (!t_wait) t_wait = now;
-                if (now - t_wait > (patient ? 900000000000ull : 20000000000ull) || ld_volatile(&ctrl->abort)) { atomicExch(&ctrl->abort, 1); s_ok = 0; break; }
+                if (now - t_wait > limit || ld_volatile(&ctrl->abort)) { atomicExch(&ctrl->abort, 1); s_ok = 0; return; }
             }
         }
+    };
+    if (blockIdx.x == 0) {
         __threadfence();
+        for (unsigned i = threadIdx.x + 1; i < gridDim.x; i += blockDim.x) wait_for(&ctrl->arrive[i].gen);
+        __syncthreads();
+        __threadfence();
+        for (unsigned i = threadIdx.x + 1; i < gridDim.x; i += blockDim.x) *(volatile unsigned long long*)&ctrl->release[i].gen = gen;
+    } else if (threadIdx.x == 0) {
+        __threadfence();
+        *(volatile unsigned long long*)&ctrl->arrive[blockIdx.x].gen = gen;
+        wait_for(&ctrl->release[blockIdx.x].gen);
+        __threadfence();
+    }
 #ifdef JTB_LV_PROF
+    if (threadIdx.x == 0) {
         s_t_leave = clock64();
         ctrl->prof_cta[blockIdx.x][1] += s_t_leave - t_arrive;
-#endif
     }
+#endif
     __syncthreads();
     return s_ok != 0;
+}
+
+__host__ __device__ inline uint64_t lv_pow2ceil(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return x <= 1 ? 1ull : 1ull << (64 - __clzll((long long)(x - 1)));
+#else
+    uint64_t s = 1;
+    while (s < x) s <<= 1;
+    return s;
+#endif
 }
 
 __host__ __device__ inline uint64_t lv_window(const LvParams& p, unsigned long long n_in, int boost) {
     uint64_t want = (uint64_t)n_in * p.slots_per_config;
     if (want < p.min_slots) want = p.min_slots;
-    uint64_t s = 1;
-    while (s < want) s <<= 1;
+    uint64_t s = lv_pow2ceil(want);
     for (int b = 0; b < boost && s < p.table_slots; ++b) s <<= 2;
     return s < p.table_slots ? s : p.table_slots;
 }
@@ -240,8 +253,9 @@ __device__ __forceinline__ void lv_advance(const LvParams& p, LvState& st, unsig
     const int o_in = st.s_in, o_out = st.s_out, o_spare = st.s_spare;
     if (flags & LV_F_GIVEUP) { st.stop = 2; st.cause = (int)(flags >> 8); return; }
     if (flags & LV_F_RETRY) {
-        if (lv_window(p, st.n_in, st.boost) >= p.table_slots) { st.stop = 2; st.cause = JTB_CAUSE_TABLE_FULL; return; }
+        if (st.win >= p.table_slots) { st.stop = 2; st.cause = JTB_CAUSE_TABLE_FULL; return; }
         st.boost++;
+        st.win = lv_window(p, st.n_in, st.boost);
         st.s_out = o_spare; st.s_spare = o_out;   // same level, same input, larger window, new epoch
         return;
     }
@@ -254,11 +268,15 @@ __device__ __forceinline__ void lv_advance(const LvParams& p, LvState& st, unsig
     st.n_in = cnt;
     st.in_idx ^= 1;
     st.contig = 0;
+    st.win = lv_window(p, st.n_in, st.boost);
     st.s_in = o_out; st.s_out = o_spare; st.s_spare = o_in;
 }
 
-template <int MODEL, int KW, bool EAGER>
-__global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(const LvParams p, const int neg_ok) {
+// NEGOK: the bank model with negative balances allowed (core.clj:217-219, the reference's default) — a transfer never
+// fails, so phase 2 needs neither the balances nor the transfer record to build a child's key.
+template <int MODEL, int KW, bool EAGER, bool NEGOK>
+__global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(const LvParams p) {
+    constexpr bool neg_ok = NEGOK;
     using L = EntryLayout<MODEL, KW>;
     constexpr int EW = L::EW;
     constexpr bool BAL = L::HAS_BAL;
@@ -278,7 +296,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
     unsigned long long bar_gen = 0;
     unsigned long long my_probes = 0;
     int my_max_probe = 0;
-    int wit_shard = -1, wit_rank = -1;   // warp-uniform filter for the witness atomicMax
+    int wit_shard = -1, wit_rank = -1;   // lane-private filter for the witness atomicMax
     if (blockIdx.x == 0 && tid == 0) ctrl->t0 = globaltimer();
     // the first input of a launch is ONE contiguous run at the start of the array
     if (tid <= LV_NSEG) s_seg_start[tid] = tid == 0 ? 0 : st.n_in;
@@ -299,16 +317,22 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
     // Chunk = G configurations for one warp (G = 1, 2, .. 32: the smallest that gives every participating warp at most
     // one chunk, so a narrow level is spread over all warps and each has few children = few probe rounds).
     auto run_attempt = [&](const LvState& a, unsigned first_chunk, unsigned chunk_stride) {
+        // G = smallest power of two >= ceil(n_in / stride), at most 32
+        unsigned G = 32, g_log = 5;
+        if (a.n_in < 32ull * chunk_stride) {
+            const unsigned q = ((unsigned)a.n_in + chunk_stride - 1) / chunk_stride;
+            g_log = q <= 1 ? 0 : 32 - __clz(q - 1);
+            G = 1u << g_log;
+        }
+        const unsigned n_chunks = (unsigned)((a.n_in + G - 1) >> g_log);
+        if (first_chunk >= n_chunks) return;   // nothing for this warp in this level
         uint64_t* out = p.buf[a.in_idx ^ 1];
         unsigned* res_flags = &ctrl->flags[a.s_out][0];
         const unsigned my_seg = first_chunk % LV_NSEG;
         unsigned long long* my_cnt = &ctrl->seg[a.s_out][my_seg].n;
         uint64_t* my_out = out + (unsigned long long)my_seg * p.seg_cap * EW;
-        const uint64_t wmask = lv_window(p, a.n_in, a.boost) - 1;
+        const uint64_t wmask = a.win - 1;
         const uint64_t tag = (uint64_t)a.epoch << 56;
-        unsigned G = 32;
-        while (G > 1 && (a.n_in + (G >> 1) - 1) / (G >> 1) <= chunk_stride) G >>= 1;
-        const unsigned n_chunks = (unsigned)((a.n_in + G - 1) / G);
         unsigned stg_head = 0, stg_tail = 0;   // warp-uniform
         auto flush = [&](unsigned n) {
             unsigned long long base = 0;
@@ -397,7 +421,6 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 Child<KW> ch;
                 bool is_new = false;
                 int owner = 0;
-                int adv_shard = -1, adv_rank = -1;
                 if (act) {
                     int lo = 0, hi = 32;       // largest o with start[o] <= g
                     while (hi - lo > 1) {
@@ -409,7 +432,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     Expander<MODEL, KW, EAGER> Y;
 #pragma unroll
                     for (int i = 0; i < KW; ++i) Y.w[i] = S.w[owner][i];
-                    if constexpr (BAL) {
+                    if constexpr (BAL && !NEGOK) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) Y.bal[i] = S.bal[owner][i];
                     }
@@ -423,8 +446,8 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     const int ns = __popcll(otodo);
                     bool ok;
                     int t_slot = 0;
-                    if (k < ns) { t_slot = select64(otodo, k); ok = Y.child_slot(T, t_slot, neg_ok != 0, ch, true); }
-                    else ok = Y.child_class(T, select64(S.cls_todo[owner], k - ns), neg_ok != 0, ch);
+                    if (k < ns) { t_slot = select64(otodo, k); ok = Y.child_slot(T, t_slot, neg_ok, ch, true); }
+                    else ok = Y.child_class(T, select64(S.cls_todo[owner], k - ns), neg_ok, ch);
                     if (ok) {
                         if (ch.done) {
                             // every :ok op of the shard is linearized -> VALID
@@ -441,22 +464,10 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                             if constexpr (BAL) {
                                 if (is_new && ch.d < 0) Y.load_transfer(t_slot, ch);   // only NEW children need the transfer
                             }
-                            if (is_new && ch.cgj > Y.gj) { adv_shard = Y.shard; adv_rank = ch.cgj; }
-                        }
-                    }
-                }
-                // ---- witness bookkeeping: furthest frontier reached (one RED per warp and advance, not per lane) ----
-                {
-                    const int best = __reduce_max_sync(FULL, adv_rank);
-                    if (best >= 0) {
-                        const unsigned who = __ballot_sync(FULL, adv_rank == best);
-                        const int bshard = __shfl_sync(FULL, adv_shard, __ffs(who) - 1);
-                        const bool mixed = __any_sync(FULL, adv_rank >= 0 && adv_shard != bshard);
-                        if (mixed) {   // several shards in one round (multi-key histories): every lane for itself
-                            if (adv_rank >= 0) atomicMax(&p.shard_max_rank[adv_shard], adv_rank);
-                        } else if (wit_shard != bshard || wit_rank < best) {
-                            wit_shard = bshard; wit_rank = best;
-                            if (lane == 0) atomicMax(&p.shard_max_rank[bshard], best);
+                            if (is_new && ch.cgj > Y.gj && (wit_shard != Y.shard || wit_rank < ch.cgj)) {
+                                wit_shard = Y.shard; wit_rank = ch.cgj;   // furthest frontier reached: the witness
+                                atomicMax(&p.shard_max_rank[Y.shard], ch.cgj);
+                            }
                         }
                     }
                 }
@@ -545,7 +556,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
         if (st.stop) break;
         const bool narrow = st.n_in <= p.narrow_max;
         {   // a window larger than what is initialised: clear the new part first (wide attempts only; rare)
-            const uint64_t win = lv_window(p, st.n_in, st.boost);
+            const uint64_t win = st.win;
             if (win > st.zeroed) {
                 zero_fill(st.zeroed, win);
                 st.zeroed = win;
@@ -559,8 +570,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     if (p.time_budget_ns && globaltimer() - ctrl->t0 > p.time_budget_ns)
                         atomicOr(&ctrl->flags[st.s_out][0], LV_F_GIVEUP | ((unsigned)JTB_CAUSE_BUDGET << 8));
                     if (st.n_in > ctrl->max_width) ctrl->max_width = st.n_in;
-                    const uint64_t win = lv_window(p, st.n_in, st.boost);
-                    if (win > ctrl->max_window) ctrl->max_window = win;
+                    if (st.win > ctrl->max_window) ctrl->max_window = st.win;
                 }
             }
 #ifdef JTB_LV_PROF
@@ -592,7 +602,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     run_attempt(st, (unsigned)warp, (unsigned)LV_WARPS);
                     __syncthreads();
                     collect(st);
-                    if (st.stop || st.n_in > p.narrow_max || lv_window(p, st.n_in, st.boost) > st.zeroed) break;
+                    if (st.stop || st.n_in > p.narrow_max || st.win > st.zeroed) break;
                 }
                 if (tid == 0) {
                     ctrl->pub = st;

@@ -484,6 +484,15 @@ bool prepare(const jtb_history* h, const jtb_model* m, Prepared& out) {
             std::memcpy(row + 18, &fast, 8);
         }
     }
+    {
+        unsigned long long open_sum = 0;
+        for (int64_t g = 0; g < out.n_ranks; ++g) {
+            uint64_t occ;
+            std::memcpy(&occ, &out.rows[(size_t)g * RW + 14], 8);
+            open_sum += (unsigned)__builtin_popcountll(occ);
+        }
+        out.mean_open = out.n_ranks ? (double)open_sum / (double)out.n_ranks : 0.0;
+    }
     return true;
 }
 

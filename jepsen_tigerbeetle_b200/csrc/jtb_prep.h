@@ -90,6 +90,7 @@ struct Prepared {
     std::vector<int32_t> shard_cause; // JTB_CAUSE_* decided on the host (too wide), else 0
     std::vector<int32_t> max_classes; // classes per shard
     int max_nc = 0;                   // max classes in any shard
+    double mean_open = 0;             // mean number of open (linearizable) ops per frontier row: how wide the search gets
     std::string error;
 };
 
