@@ -25,9 +25,11 @@ sharded  : beside the headline every line carries `"sharded"`: BASELINE configs 
 --impl reference : the CPU restatement of knossos.wgl (oracle/, kind "port" — the reference's own
            implementation is JVM-only and cannot run here) on the same history, each step a bounded
            sample (first --ref-configs configurations) on one thread per key like knossos.wgl (N keys ->
-           N threads); ONE full run to the verdict is timed beside it (`time_to_verdict_s`, rank 0 only,
-           key 1) so that the driver's record carries a verdict-to-verdict ratio.  Its `sharded` object
-           runs the same C5 / C4 histories over min(16 N, host cores) threads (independent/checker's fan-out).
+           N threads); it cannot reach the verdict of the headline instance (`time_to_verdict_s` null,
+           `did_not_finish` says why), so ONE full run of the tau_think 5 ms instance is timed beside it
+           (`verdict_to_verdict`, rank 0 only) — the same block the GPU arm prints: a verdict-to-verdict
+           ratio on an instance both arms finish.  Its `sharded` object runs the same C5 / C4 histories
+           over min(16 N, host cores) threads (independent/checker's fan-out).
 """
 import argparse
 import json
@@ -363,6 +365,9 @@ def main():
         peak, peak_src = peak_hbm()
         achieved = bytes_t / world / kern_max / 1e9  # per GPU, GB/s (algorithmic bytes / launch time)
         tr = traffic_from_profile()
+        if tr and not (args.think_ms == tr.get("think_ms", 0.0) and args.ops == 10000 and args.clients == 32
+                       and not args.eager_reads and not args.invalid):
+            tr = None   # the capture is of the default workload only
         line = {
             "metric": METRIC, "value": configs_t / kern_max, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps,
