@@ -118,6 +118,11 @@ typedef struct jtb_model {
  * Verdict, witness and exhaustive configuration counts are identical; the bits force one engine. */
 #define JTB_OPT_ENGINE_LEVEL    4
 #define JTB_OPT_ENGINE_WORKLIST 8
+/* Histories with crashed (:info) ops of at most 16 keys are first swept by a BEAM (the level engine expanding only the
+ * best ~1k, then ~16k configurations of every level: fewest crashed ops consumed, furthest frontier): it finds the
+ * linearization of a valid history in milliseconds where an exhaustive search drowns.  A beam can only ever report
+ * VALID; keys it does not decide go to the exhaustive search.  Set this flag to skip it. */
+#define JTB_OPT_NO_BEAM         16
 
 /* Options for a context.  Zero-initialise, then set what you need. */
 typedef struct jtb_opts {

@@ -19,7 +19,8 @@ public final class Native {
     private Native() {}
 
     /** {@code jtb_opts.flags} bits (include/jtb_check.h). */
-    public static final int OPT_NO_EAGER_READS = 1, OPT_NO_SCOUTS = 2, OPT_ENGINE_LEVEL = 4, OPT_ENGINE_WORKLIST = 8;
+    public static final int OPT_NO_EAGER_READS = 1, OPT_NO_SCOUTS = 2, OPT_ENGINE_LEVEL = 4, OPT_ENGINE_WORKLIST = 8,
+            OPT_NO_BEAM = 16;
 
     /** Number of CUDA devices ({@code jtb_device_count}). */
     public static native int deviceCount();

@@ -10,6 +10,7 @@ OPT_NO_EAGER_READS = 1
 OPT_NO_SCOUTS = 2
 OPT_ENGINE_LEVEL = 4
 OPT_ENGINE_WORKLIST = 8
+OPT_NO_BEAM = 16
 
 CAUSE_NONE, CAUSE_TABLE_FULL, CAUSE_BUDGET, CAUSE_TOO_WIDE = 0, 1, 2, 3
 CAUSE_NAME = {0: None, 1: "table-full", 2: "budget", 3: "too-wide"}

@@ -38,9 +38,10 @@ struct jtb_ctx {
     DevBuf sc_init, sc_tables, sc_stacks, sc_ctl;   // scouts: initial entries, private tables, stacks, control words
     SfBuffers sf;                        // set-full pass: its device buffers
     DevBuf lv_ctrl, lv_buf[2];          // level engine: control block, the two level arrays
+    DevBuf lv_aux[2], lv_beam;          // beam mode: per-entry priority words, histogram + trackers
     size_t table_dirty = ~(size_t)0;    // bytes at the start of `table` that may hold old slots (level engine clears only these)
     int last_engine = 0;                // 0 work-list (visited table complete), 1 level (visited set is ephemeral)
-    unsigned long long stats[20] = {0};
+    unsigned long long stats[24] = {0};
     unsigned long long last_configs = 0;  // configs of the previous search (sizes the next table)
     // what jtb_final_configs needs from the last search (its visited table is still in `table`)
     struct {
@@ -182,8 +183,10 @@ int launch_level_kw(jtb_ctx* ctx, int kw, const LvParams& p, int neg_ok, bool ea
 // The search is ONE cooperative launch.  Only when a level outgrows the level arrays or the hash window does the kernel
 // stop (cause TABLE_FULL) with the level it could not finish intact in its input array; the host then allocates 4x
 // larger buffers, copies that one level over and relaunches from there.
+// beam_w > 0: beam mode (jtb_level.cuh) — not exhaustive: only a VALID answer (shard_found) means anything.
 int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shards, const std::vector<int>& searchable,
-                 const std::vector<uint64_t>& init_entries, Ctrl& hc, double& kernel_s, uint64_t& configs, uint64_t& probes) {
+                 const std::vector<uint64_t>& init_entries, Ctrl& hc, double& kernel_s, uint64_t& configs, uint64_t& probes,
+                 uint32_t beam_w = 0) {
     const int KW = P.key_words;
     const bool bank = m->kind == JTB_MODEL_BANK;
     const int EW = KW + (bank ? 4 : 0);
@@ -210,6 +213,19 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         ensure(ctx, ctx->lv_ctrl, sizeof(LvCtrl)))
         return -1;
     uint64_t buf_cap = std::min(ctx->lv_buf[0].cap, ctx->lv_buf[1].cap) / ((size_t)EW * 8);
+    if (beam_w) {
+        if (ensure(ctx, ctx->lv_aux[0], buf_cap * 4 + 64) || ensure(ctx, ctx->lv_aux[1], buf_cap * 4 + 64) ||
+            ensure(ctx, ctx->lv_beam, sizeof(LvBeam)))
+            return -1;
+        std::vector<LvBeam> hb(1);
+        std::memset(hb.data(), 0, sizeof(LvBeam));
+        for (int k = 0; k < 3; ++k)
+            for (int s = 0; s < LV_BEAM_SHARDS; ++s) { hb[0].min_crashed[k][s] = 0x7fffffff; hb[0].max_rank[k][s] = -1; }
+        for (int s : searchable) { hb[0].min_crashed[0][s] = 0; hb[0].max_rank[0][s] = (int)P.rank_base[s]; }
+        CK(cudaMemcpyAsync(ctx->lv_beam.p, hb.data(), sizeof(LvBeam), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->lv_aux[0].p, 0, init_entries.size() / EW * 4 + 64, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // `hb` must outlive the copy
+    }
     // only what an earlier search may have written is cleared (the rest of the table is still zero)
     CK(cudaMemsetAsync(ctx->table.p, 0, std::min(ctx->table_dirty, (size_t)table_slots * KW * 8), ctx->stream));
     ctx->table_dirty = 0;
@@ -238,6 +254,11 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
     p.init.epoch = 1;
     p.init.s_in = 0; p.init.s_out = 1; p.init.s_spare = 2;
     p.init.contig = 1;
+    p.init.beam_thr = -1;
+    p.beam_w = beam_w;
+    p.aux[0] = (uint32_t*)ctx->lv_aux[0].p;
+    p.aux[1] = (uint32_t*)ctx->lv_aux[1].p;
+    p.beam = (LvBeam*)ctx->lv_beam.p;
     p.init.win = 0;   // (set per launch below: needs the table size)
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     int attempts = 0, grid = 0;
@@ -288,6 +309,7 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         narrow_levels += lc.narrow_levels;
         ctx->table_dirty = std::max(ctx->table_dirty, (size_t)std::max<uint64_t>(lc.max_window, p.min_slots) * KW * 8);
         if (!(lc.fin.stop == 2 && lc.fin.cause == JTB_CAUSE_TABLE_FULL)) break;
+        if (beam_w) break;   // a beam that outgrows its arrays has failed as a beam: the caller falls back
         // ---- a level outgrew the arrays or the window: 4x of both, carry the unfinished level over -------------
         CK(cudaMemGetInfo(&free_b, &total_b));
         const size_t have = ctx->table.cap + ctx->lv_buf[0].cap + ctx->lv_buf[1].cap;
@@ -482,7 +504,7 @@ void jtb_destroy(jtb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     DevBuf* bufs[] = {&ctx->table, &ctx->pool, &ctx->rows, &ctx->classes, &ctx->cls_inv, &ctx->ctrl, &ctx->found,
                       &ctx->maxrank, &ctx->sc_init, &ctx->sc_tables, &ctx->sc_stacks, &ctx->sc_ctl, &ctx->lv_ctrl,
-                      &ctx->lv_buf[0], &ctx->lv_buf[1]};
+                      &ctx->lv_buf[0], &ctx->lv_buf[1], &ctx->lv_aux[0], &ctx->lv_aux[1], &ctx->lv_beam};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     ctx->sf.release();
@@ -530,8 +552,7 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
     // initial configurations: one per shard that has completed ops
     std::vector<uint64_t> init_entries;
     std::vector<int> searchable;
-    for (int s = 0; s < n_shards; ++s) {
-        if (P.shard_cause[s] || P.rank_base[s + 1] == P.rank_base[s]) continue;
+    auto add_init = [&](int s) {
         searchable.push_back(s);
         std::vector<uint64_t> e(EW, 0);
         e[0] = KEY_VALID | ((uint64_t)(uint32_t)P.rank_base[s] << 32) |
@@ -541,7 +562,9 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
                 e[KW + i] = (uint64_t)(uint32_t)m->init_balance[2 * i] |
                             ((uint64_t)(uint32_t)m->init_balance[2 * i + 1] << 32);
         init_entries.insert(init_entries.end(), e.begin(), e.end());
-    }
+    };
+    for (int s = 0; s < n_shards; ++s)
+        if (!P.shard_cause[s] && P.rank_base[s + 1] != P.rank_base[s]) add_init(s);
     double kernel_s = 0;
     uint64_t configs = 0, probes = 0;
     ctx->stats[10] = 0;
@@ -558,8 +581,51 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         if (ensure(ctx, ctx->ctrl, sizeof(Ctrl)) || ensure(ctx, ctx->found, n_shards * sizeof(int)) ||
             ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
             return -1;
-        // ---- engine: level-synchronous sweep (jtb_level.cuh) or work list (jtb_wgl.cuh / jtb_search.cuh) ----------
         const bool eager_mode = !(ctx->opts.flags & JTB_OPT_NO_EAGER_READS);
+        // ---- beam first (histories with crashed ops, <= 16 keys): finds the linearization of a VALID history in a few
+        //      thousand narrow levels where an exhaustive search visits 10^8..10^10 configurations; keys it decides are
+        //      VALID, the others go on to the exhaustive engine below ------------------------------------------------
+        std::vector<char> beam_found(n_shards, 0);
+        double beam_kernel_s = 0;
+        unsigned long long beam_configs = 0, beam_levels = 0, beam_attempts = 0, beam_decided = 0, beam_probes = 0;
+        ctx->stats[20] = ctx->stats[21] = ctx->stats[22] = ctx->stats[23] = 0;
+        if (P.max_nc > 0 && P.max_nc <= 64 && n_shards <= LV_BEAM_SHARDS && P.n_ranks < LV_MAX_RANKS && !force_engine &&
+            !(ctx->opts.flags & (JTB_OPT_NO_BEAM | JTB_OPT_ENGINE_LEVEL | JTB_OPT_ENGINE_WORKLIST)) && !getenv("JTB_NO_BEAM") &&
+            !getenv("JTB_SCOUT_ONLY") && !getenv("JTB_ENGINE")) {
+            const uint32_t widths[2] = {1024u, 16384u};
+            for (int wi = 0; wi < 2 && !searchable.empty(); ++wi) {
+                CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));
+                for (int s = 0; s < n_shards; ++s) h_max[s] = (int)P.rank_base[s];
+                CK(cudaMemcpyAsync(ctx->maxrank.p, h_max.data(), n_shards * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                Ctrl bhc;
+                double ks = 0;
+                uint64_t bc = 0, bp = 0;
+                if (int rc = search_level(ctx, m, P, n_shards, searchable, init_entries, bhc, ks, bc, bp, widths[wi])) return rc;
+                CK(cudaMemcpyAsync(h_found.data(), ctx->found.p, n_shards * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                beam_kernel_s += ks; beam_configs += bc; beam_probes += bp; beam_levels += ctx->stats[2]; ++beam_attempts;
+                std::vector<int> left;
+                for (int s : searchable) {
+                    if (h_found[s]) { beam_found[s] = 1; ++beam_decided; }
+                    else left.push_back(s);
+                }
+                searchable.clear();
+                init_entries.clear();
+                for (int s : left) add_init(s);
+            }
+            ctx->stats[20] = beam_levels; ctx->stats[21] = beam_configs; ctx->stats[22] = beam_decided; ctx->stats[23] = beam_attempts;
+            std::fill(h_found.begin(), h_found.end(), 0);
+            for (int s = 0; s < n_shards; ++s) h_max[s] = 0;
+            if (searchable.empty()) {   // every key decided by the beam
+                kernel_s = beam_kernel_s; configs = beam_configs; probes = beam_probes;
+                std::memset(&hc, 0, sizeof hc);
+                hc.stop = 1;
+                ctx->stats[19] = 1;
+                ctx->last_engine = 1;
+            }
+        }
+        if (!searchable.empty()) {
+        // ---- engine: level-synchronous sweep (jtb_level.cuh) or work list (jtb_wgl.cuh / jtb_search.cuh) ----------
         // Default choice (measured, profiles/r2_engines.md): histories with crashed ops -> work list (its depth-first
         // order + scouts find the linearization of a valid history long before a breadth-first sweep would);
         // Knossos-exact space -> level engine (wide levels: 1.2-4 G configs/s against 0.9, bounded memory);
@@ -846,6 +912,10 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
             st[15] = sc_ctl[2]; st[16] = sc_ctl[3]; st[17] = sc_ctl[4]; st[18] = (unsigned long long)n_scouts;
         }
         }   // engine
+        kernel_s += beam_kernel_s;
+        }   // something left for the exhaustive engines
+        for (int s = 0; s < n_shards; ++s)
+            if (beam_found[s]) shards[s].valid = JTB_VALID;
         if (hc.stop == 2 && hc.cause == CAUSE_RING_FULL) hc.cause = JTB_CAUSE_BUDGET;
         if (hc.overflow) {   // a ring slot was overwritten before it was consumed: no verdict may be derived from this search
             hc.stop = 2;
@@ -1071,7 +1141,7 @@ double jtb_prepare_info(const jtb_history* h, const jtb_model* m, long long info
 
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n) {
     if (!ctx) return -1;
-    for (int i = 0; i < n && i < 20; ++i) out[i] = ctx->stats[i];
+    for (int i = 0; i < n && i < 24; ++i) out[i] = ctx->stats[i];
     return 0;
 }
 

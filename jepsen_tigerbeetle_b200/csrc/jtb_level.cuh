@@ -52,12 +52,30 @@ constexpr unsigned LV_F_DECIDED = 1, LV_F_GIVEUP = 2, LV_F_RETRY = 4;   // resul
 struct LvSeg {
     alignas(128) unsigned long long n;   // entries appended to this segment of the next level
 };
+// Beam mode (histories with crashed ops): of every level only the ~beam_w best configurations per undecided shard are
+// expanded — fewest crashed ops consumed first, then furthest frontier (relative to the shard's best in that level).
+// A beam can only ever find a linearization (VALID); when it dies the host falls back to an exhaustive engine.
+constexpr int LV_BEAM_BINS = 1024;      // 16 crashed-op steps x 64 rank steps
+constexpr int LV_BEAM_SHARDS = 16;      // beam mode handles histories of at most this many keys
+struct LvBeam {
+    unsigned hist[3][LV_BEAM_BINS];     // priority histogram of the configurations appended (set = the attempt's output role)
+    int min_crashed[3][LV_BEAM_SHARDS]; // per shard: fewest crashed ops consumed among them
+    int max_rank[3][LV_BEAM_SHARDS];    //            furthest frontier among them
+};
+__host__ __device__ inline int lv_beam_key(int crashed, int min_crashed, int rank, int max_rank) {
+    int c = crashed - min_crashed, r = max_rank + 2 - rank;
+    c = c < 0 ? 0 : (c > 15 ? 15 : c);
+    r = r < 0 ? 0 : (r > 63 ? 63 : r);
+    return c * 64 + r;   // smaller = better
+}
+
 struct LvState {   // identical in every thread of the grid
     unsigned long long level, attempt, n_in, total;
     int epoch, in_idx, boost, stop, cause;
     int s_in, s_out, s_spare;    // roles of the three counter sets: input counts / this attempt's output / being reset
     int contig;                  // the input is still the launch's contiguous run (not segmented)
     unsigned long long win;      // hash window (slots) of the attempt this state describes = lv_window(n_in, boost)
+    int beam_thr, pad_;          // beam mode: input configurations with a priority key above this are dropped (-1: keep all)
     unsigned long long zeroed;   // table slots known to be initialised
 };
 struct LvRelease {
@@ -86,6 +104,9 @@ struct LvParams {
     uint64_t* table;
     uint64_t table_slots;     // capacity (power of two)
     uint64_t* buf[2];         // level arrays, entries of EW words
+    uint32_t* aux[2];         // beam mode: crashed ops consumed, one word per entry of buf[]
+    LvBeam* beam;             // beam mode: histogram + per-shard trackers
+    uint32_t beam_w;          // beam width per undecided shard (0 = exhaustive sweep)
     uint64_t buf_cap;         // entries per array
     uint64_t seg_cap;         // = buf_cap / LV_NSEG: entries per output segment
     LvCtrl* ctrl;
@@ -107,6 +128,8 @@ struct LvScratch {   // per warp, shared memory
     int32_t bal[BAL ? 32 : 1][8];
     int32_t hdr[32][6];     // fr_pos, shard, gj_end, cls_base, rslot, ncls
     uint32_t start[36];     // exclusive prefix of the child counts; [32] = total
+    uint32_t crashed[32];   // beam mode: crashed ops consumed by each configuration of the chunk
+    uint32_t stage_aux[LV_STAGE];
     uint64_t stage[LV_STAGE][EW];
 };
 
@@ -268,6 +291,7 @@ __device__ __forceinline__ void lv_advance(const LvParams& p, LvState& st, unsig
     st.n_in = cnt;
     st.in_idx ^= 1;
     st.contig = 0;
+    st.beam_thr = -1;
     st.win = lv_window(p, st.n_in, st.boost);
     st.s_in = o_out; st.s_out = o_spare; st.s_spare = o_in;
 }
@@ -303,14 +327,15 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
     __syncthreads();
 
     // Where the idx-th configuration of the level lives: segment by binary search in the prefix, then the offset.
-    auto entry_of = [&](const LvState& a, unsigned long long idx) -> const uint64_t* {
+    auto entry_of = [&](const LvState& a, unsigned long long idx, unsigned long long& eidx) -> const uint64_t* {
         int lo = 0, hi = LV_NSEG;       // largest s with seg_start[s] <= idx
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (s_seg_start[mid] <= idx) lo = mid; else hi = mid;
         }
         // (a launch's first input is one contiguous run: prefix [0, n, n, ...] puts all of it in "segment 0" at offset 0)
-        return p.buf[a.in_idx] + ((unsigned long long)lo * p.seg_cap + (idx - s_seg_start[lo])) * EW;
+        eidx = (unsigned long long)lo * p.seg_cap + (idx - s_seg_start[lo]);
+        return p.buf[a.in_idx] + eidx * EW;
     };
 
     // ---- one level attempt over the chunks [first, first + stride, ...) of the input array -------------------
@@ -334,6 +359,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
         const uint64_t wmask = a.win - 1;
         const uint64_t tag = (uint64_t)a.epoch << 56;
         unsigned stg_head = 0, stg_tail = 0;   // warp-uniform
+        int bt_shard = -1, bt_min = 0x7fffffff, bt_max = -1;   // beam: lane-private filter for the tracker atomics
         auto flush = [&](unsigned n) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(my_cnt, (unsigned long long)n);
@@ -344,6 +370,8 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     const unsigned e = x / EW, k = x - e * EW;
                     dst[x] = S.stage[(stg_head + e) % LV_STAGE][k];
                 }
+                if (p.beam_w && (unsigned)lane < n)
+                    p.aux[a.in_idx ^ 1][(unsigned long long)my_seg * p.seg_cap + base + lane] = S.stage_aux[(stg_head + lane) % LV_STAGE];
             }   // else: the count beyond seg_cap is seen by everyone after the barrier (TABLE_FULL -> the host grows)
             stg_head += n;
             __syncwarp();
@@ -362,7 +390,10 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 X.todo = 0; X.rd_ok = 0; X.ncls = 0; X.cls_i = 0;
                 X.fr_pos = 0; X.shard = 0; X.gj_end = 0; X.cls_base = 0; X.rslot = 0;
                 if (have) {
-                    const uint64_t* e = entry_of(a, idx);
+                    unsigned long long eidx;
+                    const uint64_t* e = entry_of(a, idx, eidx);
+                    unsigned crashed = 0;
+                    if (p.beam_w) crashed = __ldcg(p.aux[a.in_idx] + eidx);
 #pragma unroll
                     for (int i = 0; i < KW; ++i) X.w[i] = ldcg64(e + i);
                     if constexpr (BAL) {
@@ -374,7 +405,11 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                         }
                     }
                     const int shard = X.load_header(T);
-                    const bool alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
+                    bool alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
+                    if (p.beam_w) {   // aux = priority key << 16 | crashed ops consumed
+                        S.crashed[lane] = crashed & 0xffffu;
+                        if (a.beam_thr >= 0) alive = alive && (int)(crashed >> 16) <= a.beam_thr;   // outside the beam: not expanded
+                    }
                     X.begin(T, alive);
                     todo = X.todo;
                     if (X.cls_i == 0) {   // not decided, not an exclusive eager read: crashed-op classes are candidates
@@ -421,6 +456,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 Child<KW> ch;
                 bool is_new = false;
                 int owner = 0;
+                unsigned child_crashed = 0;
                 if (act) {
                     int lo = 0, hi = 32;       // largest o with start[o] <= g
                     while (hi - lo > 1) {
@@ -446,6 +482,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     const int ns = __popcll(otodo);
                     bool ok;
                     int t_slot = 0;
+                    if (p.beam_w) child_crashed = S.crashed[owner] + (k >= ns ? 1u : 0u);
                     if (k < ns) { t_slot = select64(otodo, k); ok = Y.child_slot(T, t_slot, neg_ok, ch, true); }
                     else ok = Y.child_class(T, select64(S.cls_todo[owner], k - ns), neg_ok, ch);
                     if (ok) {
@@ -468,6 +505,19 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                                 wit_shard = Y.shard; wit_rank = ch.cgj;   // furthest frontier reached: the witness
                                 atomicMax(&p.shard_max_rank[Y.shard], ch.cgj);
                             }
+                            if (is_new && p.beam_w) {
+                                // priority of the child RELATIVE TO THE INPUT LEVEL's best of its shard (the output level's
+                                // own best is only known when the level is complete), and the trackers of the output level
+                                LvBeam* bm = p.beam;
+                                const int key = lv_beam_key((int)child_crashed, __ldcg(&bm->min_crashed[a.s_in][Y.shard]), ch.cgj,
+                                                            __ldcg(&bm->max_rank[a.s_in][Y.shard]));
+                                atomicAdd(&bm->hist[a.s_out][key], 1u);
+                                child_crashed = min(child_crashed, 0xffffu) | ((unsigned)key << 16);
+                                if (bt_shard != Y.shard) { bt_shard = Y.shard; bt_min = 0x7fffffff; bt_max = -1; }
+                                const int cc = (int)(child_crashed & 0xffffu);
+                                if (cc < bt_min) { bt_min = cc; atomicMin(&bm->min_crashed[a.s_out][Y.shard], bt_min); }
+                                if (ch.cgj > bt_max) { bt_max = ch.cgj; atomicMax(&bm->max_rank[a.s_out][Y.shard], bt_max); }
+                            }
                         }
                     }
                 }
@@ -476,6 +526,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 if (newm) {
                     if (is_new) {
                         uint64_t* e = S.stage[(stg_tail + __popc(newm & lt_mask)) % LV_STAGE];
+                        if (p.beam_w) S.stage_aux[(stg_tail + __popc(newm & lt_mask)) % LV_STAGE] = child_crashed;
 #pragma unroll
                         for (int i = 0; i < KW; ++i) e[i] = ch.w[i];
                         if constexpr (BAL) {
@@ -525,6 +576,36 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
             const bool any_over = __any_sync(FULL, over);
             LvState nx = a;
             if (lane == 0) lv_advance(p, nx, t0 + t1, any_over, fl);
+            // beam mode: more configurations than the beam holds -> the largest priority key that still fits
+            int thr = -1;
+            if (p.beam_w) {
+                const unsigned long long cap = (unsigned long long)p.beam_w * (unsigned)max(1, ld_volatile(&ctrl->n_undecided));
+                if (t0 + t1 > cap) {
+                    unsigned mine = 0;   // lane owns bins [32 lane, 32 lane + 32)
+                    const unsigned* hh = p.beam->hist[a.s_out];
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) mine += *(volatile const unsigned*)&hh[lane * 32 + i];
+                    unsigned incl_h = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_up_sync(FULL, incl_h, o);
+                        if (lane >= o) incl_h += v;
+                    }
+                    // first lane whose inclusive count reaches the cap refines inside its 32 bins
+                    const unsigned reach = __ballot_sync(FULL, incl_h >= cap);
+                    if (reach) {
+                        const int wl = __ffs(reach) - 1;
+                        if (lane == wl) {
+                            unsigned long long run = incl_h - mine;
+                            int b = 0;
+                            for (; b < 32; ++b) { run += *(volatile const unsigned*)&hh[lane * 32 + b]; if (run >= cap) break; }
+                            thr = lane * 32 + min(b, 31);
+                        }
+                        thr = __shfl_sync(FULL, thr, wl);
+                    }
+                }
+            }
+            if (lane == 0 && !nx.stop && !((fl & LV_F_RETRY))) nx.beam_thr = thr;
             // the prefix belongs to the NEXT input = this output, unless the level is repeated (retry): then the old
             // prefix stays (same input)
             const bool repeated = (__shfl_sync(FULL, fl, 0) & LV_F_RETRY) != 0;
@@ -550,6 +631,10 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
         ctrl->seg[a.s_spare][lane].n = 0;
         ctrl->seg[a.s_spare][lane + 32].n = 0;
         if (lane == 0) ctrl->flags[a.s_spare][0] = 0;
+        if (p.beam_w) {
+            for (int i = lane; i < LV_BEAM_BINS; i += 32) p.beam->hist[a.s_spare][i] = 0;
+            if (lane < LV_BEAM_SHARDS) { p.beam->min_crashed[a.s_spare][lane] = 0x7fffffff; p.beam->max_rank[a.s_spare][lane] = -1; }
+        }
     };
 
     for (;;) {

@@ -96,11 +96,13 @@ class Context:
 
     def __init__(self, device: int = 0, table_bytes: int = 0, max_configs: int = 0,
                  time_budget_ms: int = 0, search_ctas: int = 0, eager_reads: bool = True,
-                 scouts: bool = True, engine: str = "auto") -> None:
-        """engine: "auto" (level engine for histories without crashed ops, work list otherwise), "level", "worklist"."""
+                 scouts: bool = True, engine: str = "auto", beam: bool = True) -> None:
+        """engine: "auto" (chosen from the history), "level", "worklist"; beam=False skips the beam
+        sweep that histories with crashed ops get first."""
         L = lib()
         flags = (0 if eager_reads else abi.OPT_NO_EAGER_READS) | (0 if scouts else abi.OPT_NO_SCOUTS)
         flags |= {"auto": 0, "level": abi.OPT_ENGINE_LEVEL, "worklist": abi.OPT_ENGINE_WORKLIST}[engine]
+        flags |= 0 if beam else abi.OPT_NO_BEAM
         opts = abi.COpts(device, flags, table_bytes, max_configs, time_budget_ms, search_ctas)
         self._h = L.jtb_create(C.byref(opts))
         if not self._h:
@@ -185,12 +187,12 @@ class Context:
         return {"total": total.value, "configs": abi.final_configs_to_list(buf, min(cap, total.value))}
 
     def stats(self) -> dict:
-        out = (C.c_ulonglong * 20)()
-        lib().jtb_get_stats(C.c_void_p(self._h), out, 20)
+        out = (C.c_ulonglong * 24)()
+        lib().jtb_get_stats(C.c_void_p(self._h), out, 24)
         names = ["configs", "probes", "expansions", "ring_tail", "ring_head", "idle_polls",
                  "max_probe_len", "table_slots", "grid", "ring_entries", "attempts", "kernel_us",
                  "h2d_bytes", "d2h_bytes", "kernel_launches", "scout_steps", "scout_configs",
-                 "scout_decided", "scouts", "engine_level"]
+                 "scout_decided", "scouts", "engine_level", "beam_levels", "beam_configs", "beam_decided", "beam_attempts"]
         return {n: int(out[i]) for i, n in enumerate(names)}
 
     # ---- K2 microbenchmark ----------------------------------------------------------------------

@@ -180,3 +180,42 @@ def test_final_configs_after_a_level_search(oracle_mod):
         fc = ctx.final_configs(h, m, 0, cap=10)
     o = oracle_mod.final_configs(h, m, 0, cap=10, eager_reads=True)
     assert fc["total"] == o["total"] and fc["configs"] == o["configs"]
+
+
+CRASH_HEAVY_VALID = [
+    synth.SynthSpec('cas-register', 2500, 24, 809007372, p_info=0.3, tau_think_ns=20e6, n_values=30),
+    synth.SynthSpec('register', 1000, 24, 902980068, p_info=0.3, tau_think_ns=5e6, n_values=30, stale_read=True),
+    synth.SynthSpec('register', 2500, 40, 321354213, p_info=0.1, tau_think_ns=20e6, n_values=30, stale_by=3),
+    synth.SynthSpec('cas-register', 1000, 16, 1, p_info=0.05),
+    synth.SynthSpec('cas-register', 50000, 64, 1, p_info=0.3, n_keys=8, grouped_keys=True),      # C5 "monster": 8 keys
+]
+
+
+@pytest.mark.parametrize("spec", CRASH_HEAVY_VALID, ids=[f"{s.model}-{s.n_ops}-{s.n_clients}-{s.p_info}" for s in CRASH_HEAVY_VALID])
+def test_beam_finds_the_linearization_of_crash_heavy_valid_histories(oracle_mod, spec):
+    """VALID histories with 5-30 % crashed ops: round 1 answered :unknown (breadth-first crowd) or needed 0.6-12 s of
+    depth-first scouts.  The beam (level engine keeping the best ~1k / ~16k configurations of every level) decides them."""
+    from jepsen_tigerbeetle_b200 import native
+    h = synth.generate(spec)
+    m = model_for(spec.model)
+    assert oracle_mod.check_linearizable(h, m, 3, eager_reads=True, max_configs=5_000_000, n_threads=8)["valid"] == H.VALID
+    with native.Context(device=0, time_budget_ms=60_000) as ctx:
+        g = ctx.check_linearizable(h, m)
+        st = ctx.stats()
+    assert g["valid"] == H.VALID, (g, st)
+    assert st["beam_decided"] == h.n_shards and st["scouts"] == 0, st
+
+
+def test_beam_never_decides_an_invalid_history(oracle_mod):
+    """A beam can only report VALID: an INVALID history with crashed ops falls through to the exhaustive search, whose
+    verdict, witness and configuration count are those of the oracle."""
+    from jepsen_tigerbeetle_b200 import native
+    h = synth.generate(synth.SynthSpec("bank", 3000, 16, 1, p_info=0.02, stale_read=True, tau_think_ns=4e6))
+    m = model_for("bank")
+    o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True, max_configs=50_000_000)
+    assert o["valid"] == H.INVALID
+    with native.Context(device=0) as ctx:
+        g = ctx.check_linearizable(h, m)
+        st = ctx.stats()
+    assert st["beam_attempts"] == 2 and st["beam_decided"] == 0, st
+    compare(g, o)

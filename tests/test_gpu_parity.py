@@ -435,12 +435,12 @@ def test_scouts_rescue_crash_heavy_valid_histories(oracle_mod):
         h = synth.generate(sp)
         m = model_for(sp.model)
         assert oracle_mod.check_linearizable(h, m, 3, eager_reads=True, max_configs=5_000_000)["valid"] == H.VALID
-        with native.Context(max_configs=50_000_000) as ctx:
+        with native.Context(max_configs=50_000_000, beam=False) as ctx:
             g = ctx.check_linearizable(h, m)
             st = ctx.stats()
         assert g["valid"] == H.VALID, (g, st)
         assert st["scouts"] == 4, st
-        with native.Context(max_configs=50_000_000, scouts=False) as ctx:
+        with native.Context(max_configs=50_000_000, scouts=False, beam=False) as ctx:
             g0 = ctx.check_linearizable(h, m)
             assert ctx.stats()["scouts"] == 0
         assert g0["valid"] in (H.VALID, H.UNKNOWN)
