@@ -255,6 +255,7 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
     p.init.s_in = 0; p.init.s_out = 1; p.init.s_spare = 2;
     p.init.contig = 1;
     p.init.beam_thr = -1;
+    p.init.beam_frac = 1024;
     p.beam_w = beam_w;
     p.aux[0] = (uint32_t*)ctx->lv_aux[0].p;
     p.aux[1] = (uint32_t*)ctx->lv_aux[1].p;
@@ -589,7 +590,7 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         double beam_kernel_s = 0;
         unsigned long long beam_configs = 0, beam_levels = 0, beam_attempts = 0, beam_decided = 0, beam_probes = 0;
         ctx->stats[20] = ctx->stats[21] = ctx->stats[22] = ctx->stats[23] = 0;
-        if (P.max_nc > 0 && P.max_nc <= 64 && n_shards <= LV_BEAM_SHARDS && P.n_ranks < LV_MAX_RANKS && !force_engine &&
+        if (P.max_nc > 0 && P.max_nc <= 64 * LV_CLS_WORDS && n_shards <= LV_BEAM_SHARDS && P.n_ranks < LV_MAX_RANKS && !force_engine &&
             !(ctx->opts.flags & (JTB_OPT_NO_BEAM | JTB_OPT_ENGINE_LEVEL | JTB_OPT_ENGINE_WORKLIST)) && !getenv("JTB_NO_BEAM") &&
             !getenv("JTB_SCOUT_ONLY") && !getenv("JTB_ENGINE")) {
             const uint32_t widths[2] = {1024u, 16384u};
@@ -638,7 +639,7 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         if (const char* en = getenv("JTB_ENGINE")) use_level = std::strcmp(en, "level") == 0;
         if (force_engine) use_level = force_engine == 1;
         if (getenv("JTB_SCOUT_ONLY")) use_level = false;                     // test hook of the work-list engine
-        if (P.n_ranks >= LV_MAX_RANKS || P.max_nc > 64) use_level = false;   // epoch tag bits / class mask width
+        if (P.n_ranks >= LV_MAX_RANKS || P.max_nc > 64 * LV_CLS_WORDS) use_level = false;   // epoch tag bits / class mask width
         ctx->stats[19] = 0;
         if (use_level) {
             CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));

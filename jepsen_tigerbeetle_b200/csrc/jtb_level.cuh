@@ -42,6 +42,7 @@ constexpr int LV_WARPS = JTB_LV_WARPS;
 constexpr int LV_THREADS = LV_WARPS * 32;
 constexpr int LV_STAGE = 64;        // staged new entries per warp (ring; flushed 32 at a time)
 constexpr int LV_MAX_PROBE = 128;
+constexpr int LV_CLS_WORDS = 4;     // 64-bit words of the per-configuration class mask: up to 256 crashed-op classes per key
 // table slots only: bits 56..61 of word 0 hold the epoch of the insertion (a key's rank must stay below 2^24)
 constexpr uint64_t LV_TAG_MASK = 0x3full << 56;
 constexpr int64_t LV_MAX_RANKS = 1ll << 24;
@@ -75,7 +76,8 @@ struct LvState {   // identical in every thread of the grid
     int s_in, s_out, s_spare;    // roles of the three counter sets: input counts / this attempt's output / being reset
     int contig;                  // the input is still the launch's contiguous run (not segmented)
     unsigned long long win;      // hash window (slots) of the attempt this state describes = lv_window(n_in, boost)
-    int beam_thr, pad_;          // beam mode: input configurations with a priority key above this are dropped (-1: keep all)
+    int beam_thr, beam_frac;     // beam mode: input configurations with a priority key above beam_thr are dropped (-1: keep
+                                 // all); of those AT beam_thr a pseudo-random beam_frac / 1024 are kept
     unsigned long long zeroed;   // table slots known to be initialised
 };
 struct LvRelease {
@@ -124,7 +126,8 @@ struct LvParams {
 template <int KW, int EW, bool BAL>
 struct LvScratch {   // per warp, shared memory
     uint64_t w[32][KW];
-    uint64_t todo[32], cls_todo[32], rd_ok[32];
+    uint64_t todo[32], rd_ok[32];
+    uint64_t cls_todo[32][LV_CLS_WORDS];   // crashed-op classes (of the configuration's shard) that yield a child
     int32_t bal[BAL ? 32 : 1][8];
     int32_t hdr[32][6];     // fr_pos, shard, gj_end, cls_base, rslot, ncls
     uint32_t start[36];     // exclusive prefix of the child counts; [32] = total
@@ -384,7 +387,8 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
             // ---------------- phase 1: lane = configuration ------------------------------------------------
             const unsigned long long idx = (unsigned long long)chunk * G + lane;
             const bool have = (unsigned)lane < G && idx < a.n_in;
-            uint64_t todo = 0, cls_todo = 0;
+            uint64_t todo = 0;
+            unsigned n_cls_children = 0;
             {
                 Expander<MODEL, KW, EAGER> X;
                 X.todo = 0; X.rd_ok = 0; X.ncls = 0; X.cls_i = 0;
@@ -408,11 +412,18 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     bool alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
                     if (p.beam_w) {   // aux = priority key << 16 | crashed ops consumed
                         S.crashed[lane] = crashed & 0xffffu;
-                        if (a.beam_thr >= 0) alive = alive && (int)(crashed >> 16) <= a.beam_thr;   // outside the beam: not expanded
+                        if (a.beam_thr >= 0) {   // outside the beam: not expanded
+                            const int key = (int)(crashed >> 16);
+                            alive = alive && (key < a.beam_thr ||
+                                              (key == a.beam_thr && (int)((hash_key<KW>(X.w) >> 17) & 1023) < a.beam_frac));
+                        }
                     }
                     X.begin(T, alive);
                     todo = X.todo;
+#pragma unroll
+                    for (int cw = 0; cw < LV_CLS_WORDS; ++cw) S.cls_todo[lane][cw] = 0;
                     if (X.cls_i == 0) {   // not decided, not an exclusive eager read: crashed-op classes are candidates
+                        uint64_t cw_bits = 0;
                         for (int ci = 0; ci < X.ncls; ++ci) {
                             const int32_t* q = reinterpret_cast<const int32_t*>(T.classes + X.cls_base + ci);
                             const I4 b = ld_i4(q + 4);
@@ -421,7 +432,8 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
 #pragma unroll
                             for (int i = 1; i < KW; ++i) if (i == b.z) field = X.w[i];
                             const int count = (int)((field >> shift) & ((1ull << width) - 1));
-                            if (count < b.y && ld_i32(T.cls_inv_pos + b.x + count) < X.fr_pos) cls_todo |= 1ull << ci;
+                            if (count < b.y && ld_i32(T.cls_inv_pos + b.x + count) < X.fr_pos) { cw_bits |= 1ull << (ci & 63); ++n_cls_children; }
+                            if ((ci & 63) == 63 || ci == X.ncls - 1) { S.cls_todo[lane][ci >> 6] = cw_bits; cw_bits = 0; }
                         }
                     }
 #pragma unroll
@@ -435,9 +447,8 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     S.hdr[lane][3] = X.cls_base; S.hdr[lane][4] = X.rslot; S.hdr[lane][5] = X.ncls;
                 }
                 S.todo[lane] = todo;
-                S.cls_todo[lane] = cls_todo;
             }
-            unsigned c = (unsigned)(__popcll(todo) + __popcll(cls_todo));
+            unsigned c = (unsigned)__popcll(todo) + n_cls_children;
             unsigned incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -484,7 +495,15 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     int t_slot = 0;
                     if (p.beam_w) child_crashed = S.crashed[owner] + (k >= ns ? 1u : 0u);
                     if (k < ns) { t_slot = select64(otodo, k); ok = Y.child_slot(T, t_slot, neg_ok, ch, true); }
-                    else ok = Y.child_class(T, select64(S.cls_todo[owner], k - ns), neg_ok, ch);
+                    else {   // (k - ns)-th candidate class: find its word, then the bit
+                        int kk = k - ns, cw = 0;
+                        for (; cw < LV_CLS_WORDS - 1; ++cw) {
+                            const int pc = __popcll(S.cls_todo[owner][cw]);
+                            if (kk < pc) break;
+                            kk -= pc;
+                        }
+                        ok = Y.child_class(T, cw * 64 + select64(S.cls_todo[owner][cw], kk), neg_ok, ch);
+                    }
                     if (ok) {
                         if (ch.done) {
                             // every :ok op of the shard is linearized -> VALID
@@ -577,7 +596,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
             LvState nx = a;
             if (lane == 0) lv_advance(p, nx, t0 + t1, any_over, fl);
             // beam mode: more configurations than the beam holds -> the largest priority key that still fits
-            int thr = -1;
+            int thr = -1, frac = 1024;
             if (p.beam_w) {
                 const unsigned long long cap = (unsigned long long)p.beam_w * (unsigned)max(1, ld_volatile(&ctrl->n_undecided));
                 if (t0 + t1 > cap) {
@@ -598,14 +617,24 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                         if (lane == wl) {
                             unsigned long long run = incl_h - mine;
                             int b = 0;
-                            for (; b < 32; ++b) { run += *(volatile const unsigned*)&hh[lane * 32 + b]; if (run >= cap) break; }
+                            unsigned in_bin = 1;
+                            for (; b < 32; ++b) {
+                                in_bin = *(volatile const unsigned*)&hh[lane * 32 + b];
+                                if (run + in_bin >= cap) break;
+                                run += in_bin;
+                            }
                             thr = lane * 32 + min(b, 31);
+                            // the boundary bin usually holds far more than what is left of the beam: keep a pseudo-random
+                            // share of it (chosen by a hash of the whole key, so related configurations are not kept or
+                            // dropped together)
+                            frac = (int)min(1024ull, (cap - min(cap, run)) * 1024ull / max(in_bin, 1u) + 1ull);
                         }
                         thr = __shfl_sync(FULL, thr, wl);
+                        frac = __shfl_sync(FULL, frac, wl);
                     }
                 }
             }
-            if (lane == 0 && !nx.stop && !((fl & LV_F_RETRY))) nx.beam_thr = thr;
+            if (lane == 0 && !nx.stop && !((fl & LV_F_RETRY))) { nx.beam_thr = thr; nx.beam_frac = frac; }
             // the prefix belongs to the NEXT input = this output, unless the level is repeated (retry): then the old
             // prefix stays (same input)
             const bool repeated = (__shfl_sync(FULL, fl, 0) & LV_F_RETRY) != 0;
