@@ -147,12 +147,15 @@ int launch_wgl_kw(jtb_ctx* ctx, int kw, const WglParams& p, int neg_ok, int grid
 template <int MODEL, int KW>
 int launch_level(jtb_ctx* ctx, const LvParams& p, int neg_ok, bool eager, int* grid_out) {
     constexpr int EW = KW + (MODEL == JTB_MODEL_BANK ? 4 : 0);
-    const size_t smem = sizeof(LvScratch<KW, EW, MODEL == JTB_MODEL_BANK>) * LV_WARPS;
+    const bool beam = p.beam_w != 0;
+    const size_t smem = (beam ? sizeof(LvScratch<KW, EW, MODEL == JTB_MODEL_BANK, true>)
+                              : sizeof(LvScratch<KW, EW, MODEL == JTB_MODEL_BANK, false>)) * LV_WARPS;
+    const bool nk = !(MODEL == JTB_MODEL_BANK && !neg_ok);
     const void* k;
-    if (MODEL == JTB_MODEL_BANK && !neg_ok)
-        k = eager ? (const void*)level_search_kernel<MODEL, KW, true, false> : (const void*)level_search_kernel<MODEL, KW, false, false>;
-    else
-        k = eager ? (const void*)level_search_kernel<MODEL, KW, true, true> : (const void*)level_search_kernel<MODEL, KW, false, true>;
+#define JTB_LVK(E, N, B) (const void*)level_search_kernel<MODEL, KW, E, (MODEL == JTB_MODEL_BANK ? N : true), B>
+    if (beam) k = eager ? (nk ? JTB_LVK(true, true, true) : JTB_LVK(true, false, true)) : (nk ? JTB_LVK(false, true, true) : JTB_LVK(false, false, true));
+    else k = eager ? (nk ? JTB_LVK(true, true, false) : JTB_LVK(true, false, false)) : (nk ? JTB_LVK(false, true, false) : JTB_LVK(false, false, false));
+#undef JTB_LVK
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LV_THREADS, smem));
@@ -289,6 +292,12 @@ int search_level(jtb_ctx* ctx, const jtb_model* m, const Prepared& P, int n_shar
         CK(cudaStreamSynchronize(ctx->stream));
         if (lc.abort) { ctx->err = "level engine: a grid barrier timed out (internal error)"; return -1; }
 #ifdef JTB_LV_PROF
+        if (beam_w && getenv("JTB_BEAM_TRACE")) {
+            for (int i = 0; i < 2048 && (i == 0 || lc.trace[i][1]); ++i)
+                if (i < 40 || i % 25 == 0)
+                    fprintf(stderr, "[beam W=%u] attempt %d level %d n_out %d thr %d frac %d min_c %d max_r %d\n", beam_w, i, lc.trace[i][0],
+                            lc.trace[i][1], lc.trace[i][2], lc.trace[i][3], lc.trace[i][4], lc.trace[i][5]);
+        }
         {
             const double wide = (double)std::max<unsigned long long>(lc.prof[9], 1), att = (double)std::max<unsigned long long>(lc.prof[8], 1);
             fprintf(stderr, "[lv prof] attempts %llu (wide %llu)  per attempt, cycles: phase1 %.0f phase2 %.0f flush %.0f | per wide level: "
@@ -593,8 +602,10 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         if (P.max_nc > 0 && P.max_nc <= 64 * LV_CLS_WORDS && n_shards <= LV_BEAM_SHARDS && P.n_ranks < LV_MAX_RANKS && !force_engine &&
             !(ctx->opts.flags & (JTB_OPT_NO_BEAM | JTB_OPT_ENGINE_LEVEL | JTB_OPT_ENGINE_WORKLIST)) && !getenv("JTB_NO_BEAM") &&
             !getenv("JTB_SCOUT_ONLY") && !getenv("JTB_ENGINE")) {
-            const uint32_t widths[2] = {1024u, 16384u};
-            for (int wi = 0; wi < 2 && !searchable.empty(); ++wi) {
+            uint32_t widths[3] = {256u, 2048u, 16384u};
+            int n_widths = 3;
+            if (const char* bw = getenv("JTB_BEAM_W")) { widths[0] = (uint32_t)std::max(1, atoi(bw)); n_widths = 1; }   // experiments
+            for (int wi = 0; wi < n_widths && !searchable.empty(); ++wi) {
                 CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));
                 for (int s = 0; s < n_shards; ++s) h_max[s] = (int)P.rank_base[s];
                 CK(cudaMemcpyAsync(ctx->maxrank.p, h_max.data(), n_shards * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -639,7 +650,7 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         if (const char* en = getenv("JTB_ENGINE")) use_level = std::strcmp(en, "level") == 0;
         if (force_engine) use_level = force_engine == 1;
         if (getenv("JTB_SCOUT_ONLY")) use_level = false;                     // test hook of the work-list engine
-        if (P.n_ranks >= LV_MAX_RANKS || P.max_nc > 64 * LV_CLS_WORDS) use_level = false;   // epoch tag bits / class mask width
+        if (P.n_ranks >= LV_MAX_RANKS || P.max_nc > 64) use_level = false;   // epoch tag bits / class mask width
         ctx->stats[19] = 0;
         if (use_level) {
             CK(cudaMemsetAsync(ctx->found.p, 0, n_shards * sizeof(int), ctx->stream));

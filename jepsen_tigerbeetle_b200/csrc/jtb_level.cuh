@@ -42,7 +42,8 @@ constexpr int LV_WARPS = JTB_LV_WARPS;
 constexpr int LV_THREADS = LV_WARPS * 32;
 constexpr int LV_STAGE = 64;        // staged new entries per warp (ring; flushed 32 at a time)
 constexpr int LV_MAX_PROBE = 128;
-constexpr int LV_CLS_WORDS = 4;     // 64-bit words of the per-configuration class mask: up to 256 crashed-op classes per key
+constexpr int LV_CLS_WORDS = 8;     // beam mode: 64-bit words of the per-configuration class mask (512 crashed-op classes
+                                    // per key); the exhaustive sweep keeps one word (64 classes, else the work list runs)
 // table slots only: bits 56..61 of word 0 hold the epoch of the insertion (a key's rank must stay below 2^24)
 constexpr uint64_t LV_TAG_MASK = 0x3full << 56;
 constexpr int64_t LV_MAX_RANKS = 1ll << 24;
@@ -95,6 +96,7 @@ struct LvCtrl {
     // -DJTB_LV_PROF builds only: cycle sums of CTA 0 / warp 0 per section, and per-CTA busy / wait cycles at barriers
     unsigned long long prof[16];
     unsigned long long prof_cta[1024][2];
+    int trace[2048][6];      // beam: per attempt (level, n_out, thr, frac, min crashed, max rank of the output)
     alignas(128) LvRelease arrive[1024];     // grid barrier: one arrival word per CTA, watched by CTA 0 ...
     alignas(128) LvRelease release[1024];    // ... and one release word per CTA, written by CTA 0
 };
@@ -123,16 +125,16 @@ struct LvParams {
     uint64_t min_slots;
 };
 
-template <int KW, int EW, bool BAL>
+template <int KW, int EW, bool BAL, bool BEAM>
 struct LvScratch {   // per warp, shared memory
     uint64_t w[32][KW];
     uint64_t todo[32], rd_ok[32];
-    uint64_t cls_todo[32][LV_CLS_WORDS];   // crashed-op classes (of the configuration's shard) that yield a child
+    uint64_t cls_todo[32][BEAM ? LV_CLS_WORDS : 1];   // crashed-op classes (of the configuration's shard) that yield a child
     int32_t bal[BAL ? 32 : 1][8];
     int32_t hdr[32][6];     // fr_pos, shard, gj_end, cls_base, rslot, ncls
     uint32_t start[36];     // exclusive prefix of the child counts; [32] = total
-    uint32_t crashed[32];   // beam mode: crashed ops consumed by each configuration of the chunk
-    uint32_t stage_aux[LV_STAGE];
+    uint32_t crashed[BEAM ? 32 : 1];   // beam mode: crashed ops consumed by each configuration of the chunk
+    uint32_t stage_aux[BEAM ? LV_STAGE : 1];
     uint64_t stage[LV_STAGE][EW];
 };
 
@@ -301,14 +303,16 @@ __device__ __forceinline__ void lv_advance(const LvParams& p, LvState& st, unsig
 
 // NEGOK: the bank model with negative balances allowed (core.clj:217-219, the reference's default) — a transfer never
 // fails, so phase 2 needs neither the balances nor the transfer record to build a child's key.
-template <int MODEL, int KW, bool EAGER, bool NEGOK>
+// BEAM: the beam mode (see LvBeam) — its own instantiation, so the exhaustive sweep pays nothing for it.
+template <int MODEL, int KW, bool EAGER, bool NEGOK, bool BEAM>
 __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(const LvParams p) {
     constexpr bool neg_ok = NEGOK;
+    constexpr int CLS_WORDS = BEAM ? LV_CLS_WORDS : 1;
     using L = EntryLayout<MODEL, KW>;
     constexpr int EW = L::EW;
     constexpr bool BAL = L::HAS_BAL;
     constexpr unsigned FULL = 0xffffffffu;
-    using Scratch = LvScratch<KW, EW, BAL>;
+    using Scratch = LvScratch<KW, EW, BAL, BEAM>;
     extern __shared__ __align__(16) unsigned char lv_smem[];
     __shared__ LvState s_state;
     __shared__ unsigned long long s_seg_start[LV_NSEG + 1];   // exclusive prefix of the input segments' counts
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     const unsigned e = x / EW, k = x - e * EW;
                     dst[x] = S.stage[(stg_head + e) % LV_STAGE][k];
                 }
-                if (p.beam_w && (unsigned)lane < n)
+                if (BEAM && (unsigned)lane < n)
                     p.aux[a.in_idx ^ 1][(unsigned long long)my_seg * p.seg_cap + base + lane] = S.stage_aux[(stg_head + lane) % LV_STAGE];
             }   // else: the count beyond seg_cap is seen by everyone after the barrier (TABLE_FULL -> the host grows)
             stg_head += n;
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     unsigned long long eidx;
                     const uint64_t* e = entry_of(a, idx, eidx);
                     unsigned crashed = 0;
-                    if (p.beam_w) crashed = __ldcg(p.aux[a.in_idx] + eidx);
+                    if constexpr (BEAM) crashed = __ldcg(p.aux[a.in_idx] + eidx);
 #pragma unroll
                     for (int i = 0; i < KW; ++i) X.w[i] = ldcg64(e + i);
                     if constexpr (BAL) {
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     }
                     const int shard = X.load_header(T);
                     bool alive = !(p.n_shards > 1 && ld_volatile(&p.shard_found[shard]));
-                    if (p.beam_w) {   // aux = priority key << 16 | crashed ops consumed
+                    if constexpr (BEAM) {   // aux = priority key << 16 | crashed ops consumed
                         S.crashed[lane] = crashed & 0xffffu;
                         if (a.beam_thr >= 0) {   // outside the beam: not expanded
                             const int key = (int)(crashed >> 16);
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     X.begin(T, alive);
                     todo = X.todo;
 #pragma unroll
-                    for (int cw = 0; cw < LV_CLS_WORDS; ++cw) S.cls_todo[lane][cw] = 0;
+                    for (int cw = 0; cw < CLS_WORDS; ++cw) S.cls_todo[lane][cw] = 0;
                     if (X.cls_i == 0) {   // not decided, not an exclusive eager read: crashed-op classes are candidates
                         uint64_t cw_bits = 0;
                         for (int ci = 0; ci < X.ncls; ++ci) {
@@ -493,11 +497,11 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                     const int ns = __popcll(otodo);
                     bool ok;
                     int t_slot = 0;
-                    if (p.beam_w) child_crashed = S.crashed[owner] + (k >= ns ? 1u : 0u);
+                    if constexpr (BEAM) child_crashed = S.crashed[owner] + (k >= ns ? 1u : 0u);
                     if (k < ns) { t_slot = select64(otodo, k); ok = Y.child_slot(T, t_slot, neg_ok, ch, true); }
                     else {   // (k - ns)-th candidate class: find its word, then the bit
                         int kk = k - ns, cw = 0;
-                        for (; cw < LV_CLS_WORDS - 1; ++cw) {
+                        for (; cw < CLS_WORDS - 1; ++cw) {
                             const int pc = __popcll(S.cls_todo[owner][cw]);
                             if (kk < pc) break;
                             kk -= pc;
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                                 wit_shard = Y.shard; wit_rank = ch.cgj;   // furthest frontier reached: the witness
                                 atomicMax(&p.shard_max_rank[Y.shard], ch.cgj);
                             }
-                            if (is_new && p.beam_w) {
+                            if (BEAM && is_new) {
                                 // priority of the child RELATIVE TO THE INPUT LEVEL's best of its shard (the output level's
                                 // own best is only known when the level is complete), and the trackers of the output level
                                 LvBeam* bm = p.beam;
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 if (newm) {
                     if (is_new) {
                         uint64_t* e = S.stage[(stg_tail + __popc(newm & lt_mask)) % LV_STAGE];
-                        if (p.beam_w) S.stage_aux[(stg_tail + __popc(newm & lt_mask)) % LV_STAGE] = child_crashed;
+                        if constexpr (BEAM) S.stage_aux[(stg_tail + __popc(newm & lt_mask)) % LV_STAGE] = child_crashed;
 #pragma unroll
                         for (int i = 0; i < KW; ++i) e[i] = ch.w[i];
                         if constexpr (BAL) {
@@ -597,7 +601,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
             if (lane == 0) lv_advance(p, nx, t0 + t1, any_over, fl);
             // beam mode: more configurations than the beam holds -> the largest priority key that still fits
             int thr = -1, frac = 1024;
-            if (p.beam_w) {
+            if constexpr (BEAM) {
                 const unsigned long long cap = (unsigned long long)p.beam_w * (unsigned)max(1, ld_volatile(&ctrl->n_undecided));
                 if (t0 + t1 > cap) {
                     unsigned mine = 0;   // lane owns bins [32 lane, 32 lane + 32)
@@ -635,6 +639,13 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
                 }
             }
             if (lane == 0 && !nx.stop && !((fl & LV_F_RETRY))) { nx.beam_thr = thr; nx.beam_frac = frac; }
+#ifdef JTB_LV_PROF
+            if (BEAM && blockIdx.x == 0 && lane == 0 && a.attempt < 2048) {
+                int* tr = ctrl->trace[a.attempt];
+                tr[0] = (int)a.level; tr[1] = (int)(t0 + t1); tr[2] = thr; tr[3] = frac;
+                tr[4] = *(volatile int*)&p.beam->min_crashed[a.s_out][0]; tr[5] = *(volatile int*)&p.beam->max_rank[a.s_out][0];
+            }
+#endif
             // the prefix belongs to the NEXT input = this output, unless the level is repeated (retry): then the old
             // prefix stays (same input)
             const bool repeated = (__shfl_sync(FULL, fl, 0) & LV_F_RETRY) != 0;
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(LV_THREADS, JTB_LV_CTAS) level_search_kernel(c
         ctrl->seg[a.s_spare][lane].n = 0;
         ctrl->seg[a.s_spare][lane + 32].n = 0;
         if (lane == 0) ctrl->flags[a.s_spare][0] = 0;
-        if (p.beam_w) {
+        if constexpr (BEAM) {
             for (int i = lane; i < LV_BEAM_BINS; i += 32) p.beam->hist[a.s_spare][i] = 0;
             if (lane < LV_BEAM_SHARDS) { p.beam->min_crashed[a.s_spare][lane] = 0x7fffffff; p.beam->max_rank[a.s_spare][lane] = -1; }
         }
