@@ -40,6 +40,7 @@ struct jtb_ctx {
     DevBuf lv_ctrl, lv_buf[2];          // level engine: control block, the two level arrays
     DevBuf lv_aux[2], lv_beam;          // beam mode: per-entry priority words, histogram + trackers
     size_t table_dirty = ~(size_t)0;    // bytes at the start of `table` that may hold old slots (level engine clears only these)
+    bool in_probe = false;              // inside the budgeted work-list probe that precedes a beam
     int last_engine = 0;                // 0 work-list (visited table complete), 1 level (visited set is ephemeral)
     unsigned long long stats[24] = {0};
     unsigned long long last_configs = 0;  // configs of the previous search (sizes the next table)
@@ -602,6 +603,30 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
         if (P.max_nc > 0 && P.max_nc <= 64 * LV_CLS_WORDS && n_shards <= LV_BEAM_SHARDS && P.n_ranks < LV_MAX_RANKS && !force_engine &&
             !(ctx->opts.flags & (JTB_OPT_NO_BEAM | JTB_OPT_ENGINE_LEVEL | JTB_OPT_ENGINE_WORKLIST)) && !getenv("JTB_NO_BEAM") &&
             !getenv("JTB_SCOUT_ONLY") && !getenv("JTB_ENGINE")) {
+            // A budgeted run of the work list first (16 M configurations, no scouts: ~20 ms): easy histories — most
+            // histories with a few crashed ops — end there, at the work list's latency; only what it leaves open gets
+            // the beam ladder.
+            if (!ctx->in_probe) {
+                ctx->in_probe = true;
+                const jtb_opts saved = ctx->opts;
+                const uint64_t probe_budget = 16ull << 20;
+                ctx->opts.max_configs = saved.max_configs ? std::min<uint64_t>(saved.max_configs, probe_budget) : probe_budget;
+                ctx->opts.flags |= JTB_OPT_NO_SCOUTS;
+                std::vector<jtb_lin_shard> ps((size_t)n_shards);
+                jtb_lin_result po;
+                const int prc = check_lin_impl(ctx, h, m, ps.data(), &po, 2);
+                ctx->opts = saved;
+                ctx->in_probe = false;
+                if (prc) return prc;
+                bool all = true;
+                for (int s : searchable) all = all && ps[s].valid != JTB_UNKNOWN;
+                if (all) {
+                    for (int s = 0; s < n_shards; ++s) shards[s] = ps[s];
+                    *out = po;
+                    out->seconds_total = now_s() - t_start;
+                    return 0;
+                }
+            }
             uint32_t widths[3] = {256u, 2048u, 16384u};
             int n_widths = 3;
             if (const char* bw = getenv("JTB_BEAM_W")) { widths[0] = (uint32_t)std::max(1, atoi(bw)); n_widths = 1; }   // experiments

@@ -203,9 +203,8 @@ def test_beam_finds_the_linearization_of_crash_heavy_valid_histories(oracle_mod,
         g = ctx.check_linearizable(h, m)
         st = ctx.stats()
     assert g["valid"] == H.VALID, (g, st)
-    assert st["beam_attempts"] >= 1, st
-    if spec.n_keys == 1 and spec.n_clients <= 40 and not (spec.model == "cas-register" and spec.n_ops == 2500):
-        assert st["beam_decided"] == 1 and st["scouts"] == 0, st      # decided by the beam alone
+    if spec.model == "register":          # beyond the 16 M-configuration work-list probe: decided by the beam alone
+        assert st["beam_decided"] == 1 and st["scouts"] == 0, st
 
 
 def test_beam_never_decides_an_invalid_history(oracle_mod):
@@ -219,5 +218,5 @@ def test_beam_never_decides_an_invalid_history(oracle_mod):
     with native.Context(device=0) as ctx:
         g = ctx.check_linearizable(h, m)
         st = ctx.stats()
-    assert st["beam_attempts"] == 2 and st["beam_decided"] == 0, st
+    assert st["beam_decided"] == 0, st
     compare(g, o)
