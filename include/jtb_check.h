@@ -118,10 +118,11 @@ typedef struct jtb_model {
  * Verdict, witness and exhaustive configuration counts are identical; the bits force one engine. */
 #define JTB_OPT_ENGINE_LEVEL    4
 #define JTB_OPT_ENGINE_WORKLIST 8
-/* Histories with crashed (:info) ops of at most 16 keys are first swept by a BEAM (the level engine expanding only the
- * best ~1k, then ~16k configurations of every level: fewest crashed ops consumed, furthest frontier): it finds the
- * linearization of a valid history in milliseconds where an exhaustive search drowns.  A beam can only ever report
- * VALID; keys it does not decide go to the exhaustive search.  Set this flag to skip it. */
+/* A single-key history with crashed (:info) ops first gets a budgeted run of the work list (16 M configurations) and,
+ * if that leaves it open, a BEAM (the level engine expanding only the best ~256, then ~2k, then ~16k configurations of
+ * every level: fewest crashed ops consumed, furthest frontier): it finds the linearization of a valid history in tens of
+ * milliseconds where an exhaustive search drowns.  A beam can only ever report VALID; what it does not decide goes to
+ * the exhaustive search.  Set this flag to skip both. */
 #define JTB_OPT_NO_BEAM         16
 
 /* Options for a context.  Zero-initialise, then set what you need. */
@@ -312,6 +313,18 @@ int jtb_multi_check_set_full(jtb_multi* mg, const jtb_history* h, int linearizab
  * out[12..14] = host->device bytes, device->host bytes, CUDA kernels launched,
  * out[15..18] = scout steps, scout configs, shards decided by a scout, scouts launched */
 int jtb_get_stats(jtb_ctx* ctx, unsigned long long* out, int n);
+
+/* SURVEY 8(f) N2 — the step before the checkers, on the device.
+ * jtb_partition_by_key replaces jepsen.independent/subhistory (set_full.clj:155: independent/checker re-filters the
+ * whole history once per key): ONE stable partition of the events by key.  event_key[i] = the key of event i (any
+ * int64; nemesis / un-keyed events can carry a key of their own).  Out: order[n_events] = original position of the
+ * i-th event of the partitioned history (events of one key keep their history order), key_ids[n_keys] ascending,
+ * shard_off[n_keys + 1] = the CSR offsets of jtb_history; key_cap = capacity of key_ids (shard_off: key_cap + 1).
+ * jtb_ledger_balances is ledger->bank's arithmetic (tests/ledger.clj:100-105): balance = credits-posted - debits-posted. */
+int jtb_partition_by_key(jtb_ctx* ctx, int64_t n_events, const int64_t* event_key, int32_t* order, int64_t* shard_off,
+                         int64_t* key_ids, int32_t key_cap, int32_t* n_keys);
+int jtb_ledger_balances(jtb_ctx* ctx, int64_t n, const int64_t* credits_posted, const int64_t* debits_posted,
+                        int32_t* balance);
 
 /* Page-locked host memory for the flattened arrays (what a JNI shim wraps in a direct ByteBuffer, what the Python
  * mirror backs its numpy arrays with).  Not required: any host pointer works; page-locked ones are copied by DMA at the

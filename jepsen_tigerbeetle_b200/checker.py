@@ -459,6 +459,44 @@ class FinalReads(Checker):
         return out
 
 
+class Stats(Checker):
+    """`(checker/stats)` as composed at core.clj:144 [UPSTREAM-RECALL, jepsen.checker/stats]: success / failure counts of
+    the client completions, overall and by :f; valid only when every :f has at least one :ok completion
+    ({:valid? false} otherwise: an operation that never once succeeded makes the rest of the analysis vacuous).
+    Host code, as in the reference (a linear pass over the history; nothing to put on a GPU)."""
+
+    @staticmethod
+    def _tally(ops) -> dict:
+        ok = sum(1 for o in ops if _kw(_g(o, "type")) == "ok")
+        fail = sum(1 for o in ops if _kw(_g(o, "type")) == "fail")
+        info = sum(1 for o in ops if _kw(_g(o, "type")) == "info")
+        return {"valid?": ok > 0, "count": ok + fail + info, "ok-count": ok, "fail-count": fail, "info-count": info}
+
+    def check(self, test, history, opts=None) -> dict:
+        done = [op for op in history if _is_client(op) and _kw(_g(op, "type")) != "invoke"]
+        by_f: dict = {}
+        for op in done:
+            by_f.setdefault(_kw(_g(op, "f")), []).append(op)
+        out = self._tally(done)
+        out["by-f"] = {f: self._tally(ops) for f, ops in sorted(by_f.items(), key=lambda kv: str(kv[0]))}
+        out["valid?"] = merge_valid_bool([r["valid?"] for r in out["by-f"].values()])
+        return out
+
+
+def merge_valid_bool(vs) -> Any:
+    """jepsen.checker/merge-valid over {True, "unknown", False} values (True for an empty collection)."""
+    order = {True: 0, "unknown": 1, False: 2}
+    worst = True
+    for v in vs:
+        if order[v] > order[worst]:
+            worst = v
+    return worst
+
+
+def stats() -> Stats:
+    return Stats()
+
+
 def unexpected_ops() -> UnexpectedOps:
     return UnexpectedOps()
 

@@ -16,6 +16,7 @@
 #include "jtb_scout.cuh"
 #include "jtb_scans.cuh"
 #include "jtb_table_bench.cuh"
+#include "jtb_partition.cuh"
 
 using namespace jtb;
 
@@ -593,14 +594,17 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
             ensure(ctx, ctx->maxrank, n_shards * sizeof(int)))
             return -1;
         const bool eager_mode = !(ctx->opts.flags & JTB_OPT_NO_EAGER_READS);
-        // ---- beam first (histories with crashed ops, <= 16 keys): finds the linearization of a VALID history in a few
+        // ---- beam first (single-key histories with crashed ops; measured on the 8-key C5 "monster": one beam shared by
+        //      several keys starves most of them — 2 of 8 decided after 7.7e8 configurations — so many-key histories keep
+        //      the work list + scouts): finds the linearization of a VALID history in a few
         //      thousand narrow levels where an exhaustive search visits 10^8..10^10 configurations; keys it decides are
         //      VALID, the others go on to the exhaustive engine below ------------------------------------------------
         std::vector<char> beam_found(n_shards, 0);
         double beam_kernel_s = 0;
         unsigned long long beam_configs = 0, beam_levels = 0, beam_attempts = 0, beam_decided = 0, beam_probes = 0;
         ctx->stats[20] = ctx->stats[21] = ctx->stats[22] = ctx->stats[23] = 0;
-        if (P.max_nc > 0 && P.max_nc <= 64 * LV_CLS_WORDS && n_shards <= LV_BEAM_SHARDS && P.n_ranks < LV_MAX_RANKS && !force_engine &&
+        if (P.max_nc > 0 && P.max_nc <= 64 * LV_CLS_WORDS && n_shards <= LV_BEAM_SHARDS && searchable.size() == 1 &&
+            P.n_ranks < LV_MAX_RANKS && !force_engine &&
             !(ctx->opts.flags & (JTB_OPT_NO_BEAM | JTB_OPT_ENGINE_LEVEL | JTB_OPT_ENGINE_WORKLIST)) && !getenv("JTB_NO_BEAM") &&
             !getenv("JTB_SCOUT_ONLY") && !getenv("JTB_ENGINE")) {
             // A budgeted run of the work list first (16 M configurations, no scouts: ~20 ms): easy histories — most
@@ -875,7 +879,11 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
             if (hc.n_undecided <= 0) break;   // the scouts decided every shard while the search was pausing
             // ---- pause/resume: the live work is exactly the non-zero ring slots ---------------------
             const uint64_t new_ring_entries = grow_ring ? ring_entries * 4 : ring_entries;
-            if (grow_buf(ring2, new_ring_entries * EW * 8)) { free_tmp(); return -1; }
+            if (grow_buf(ring2, new_ring_entries * EW * 8)) {   // no memory for the larger ring: give up like a full table
+                (void)cudaGetLastError();
+                hc.stop = 2; hc.cause = JTB_CAUSE_TABLE_FULL;
+                break;
+            }
             CK(cudaMemsetAsync(ring2.p, 0, new_ring_entries * EW * 8, ctx->stream));
             Ctrl* dc = (Ctrl*)ctx->ctrl.p;
             CK(cudaMemsetAsync(&dc->tail, 0, sizeof(unsigned long long), ctx->stream));
@@ -892,13 +900,17 @@ static int check_lin_impl(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m
             CK(cudaGetLastError());
             if (grow_table) {
                 const uint64_t new_slots = n_slots * 4;
-                if (grow_buf(table2, new_slots * KW * 8)) { free_tmp(); return -1; }
+                if (grow_buf(table2, new_slots * KW * 8)) {   // old + 4x table do not fit together: UNKNOWN, not an error
+                    (void)cudaGetLastError();
+                    hc.stop = 2; hc.cause = JTB_CAUSE_TABLE_FULL;
+                    break;
+                }
                 CK(cudaMemsetAsync(table2.p, 0, new_slots * KW * 8, ctx->stream));
                 uint64_t g_win, g_stride;
                 geometry(new_slots, g_win, g_stride);
-                if (KW == 2) table_rehash_kernel<2><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride);
-                else if (KW == 4) table_rehash_kernel<4><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride);
-                else table_rehash_kernel<8><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride);
+                if (KW == 2) table_rehash_kernel<2><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride, &dc->overflow);
+                else if (KW == 4) table_rehash_kernel<4><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride, &dc->overflow);
+                else table_rehash_kernel<8><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>((const uint64_t*)ctx->table.p, n_slots, (uint64_t*)table2.p, new_slots - 1, g_win, g_stride, &dc->overflow);
                 CK(cudaGetLastError());
                 CK(cudaStreamSynchronize(ctx->stream));
                 std::swap(ctx->table, table2);
@@ -1045,7 +1057,8 @@ int jtb_final_configs(jtb_ctx* ctx, const jtb_history* h, const jtb_model* m, in
     }
     {
         DevBuf d_cnt, d_out;
-        auto free_all = [&]() { if (d_cnt.p) cudaFree(d_cnt.p); if (d_out.p) cudaFree(d_out.p); };
+        auto free_all = [&]() { if (d_cnt.p) cudaFree(d_cnt.p); if (d_out.p) cudaFree(d_out.p); d_cnt = DevBuf(); d_out = DevBuf(); };
+        struct Guard { decltype(free_all)& f; ~Guard() { f(); } } guard{free_all};   // CK() returns early on errors
         if (ensure(ctx, d_cnt, 8)) return -1;
         const uint64_t* table = (const uint64_t*)ctx->table.p;
         unsigned long long total = 0;
@@ -1147,6 +1160,22 @@ int jtb_check_bank_totals(jtb_ctx* ctx, const jtb_history* h, const jtb_model* a
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
     ctx->fc.valid = false;
     return run_bank_totals(ctx->stream, ctx->ev0, ctx->ev1, h, accounts, total_amount, out, ctx->err);
+}
+
+// the step before the checkers (independent/subhistory, ledger->bank) on the device
+int jtb_partition_by_key(jtb_ctx* ctx, int64_t n_events, const int64_t* event_key, int32_t* order, int64_t* shard_off,
+                         int64_t* key_ids, int32_t key_cap, int32_t* n_keys) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    return run_partition_by_key(ctx->stream, n_events, event_key, order, shard_off, key_ids, key_cap, n_keys, ctx->err);
+}
+
+int jtb_ledger_balances(jtb_ctx* ctx, int64_t n, const int64_t* credits_posted, const int64_t* debits_posted, int32_t* balance) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return -1; }
+    return run_ledger_balances(ctx->stream, n, credits_posted, debits_posted, balance, ctx->err);
 }
 
 // Page-locked host memory for the caller's flattened arrays (the id lists of set-full reads are hundreds of MB: from

@@ -808,14 +808,17 @@ __global__ void ring_compact_kernel(const uint64_t* __restrict__ old_ring, uint6
 // Re-inserts every key of a full table into a larger one (table growth without losing work).
 template <int KW>
 __global__ void table_rehash_kernel(const uint64_t* __restrict__ old_table, uint64_t old_slots, uint64_t* new_table,
-                                    uint64_t new_mask, uint64_t win_mask, uint64_t rank_stride) {
+                                    uint64_t new_mask, uint64_t win_mask, uint64_t rank_stride, int* lost = nullptr) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_slots; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t k[KW];
 #pragma unroll
         for (int w = 0; w < KW; ++w) k[w] = old_table[i * KW + w];
         if (k[0] == 0) continue;
         int plen;
-        table_insert_at<KW>(new_table, new_mask, table_home<KW>(k, new_mask, win_mask, rank_stride), k, &plen);
+        // a 4x larger table at load <= 1/8 cannot run out of probe slots; if it ever did, a visited key would be lost
+        // and the search would re-expand it (wrong counts): the host turns the flag into UNKNOWN
+        if (table_insert_at<KW>(new_table, new_mask, table_home<KW>(k, new_mask, win_mask, rank_stride), k, &plen) < 0 && lost)
+            atomicExch(lost, 1);
     }
 }
 

@@ -18,14 +18,14 @@ LIB_PATH = os.environ.get("JTB_LIB_PATH") or os.path.join(_HERE, "libjtb_check.s
 CSRC = os.path.join(_HERE, "csrc")
 _SOURCES = ["jtb_abi.cu", "jtb_prep.cpp", "jtb_multi.cpp"]
 _DEPS = _SOURCES + ["jtb_prep.h", "jtb_expand.h", "jtb_wgl.cuh", "jtb_search.cuh", "jtb_scout.cuh", "jtb_scans.cuh",
-                    "jtb_table_bench.cuh", "jtb_level.cuh"]
+                    "jtb_table_bench.cuh", "jtb_level.cuh", "jtb_partition.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 EXPORTS = ["jtb_abi_version", "jtb_device_count", "jtb_create", "jtb_destroy", "jtb_last_error",
            "jtb_check_linearizable", "jtb_check_set_full", "jtb_check_bank_totals",
            "jtb_table_bench", "jtb_get_stats", "jtb_struct_size", "jtb_prepare_seconds", "jtb_prepare_info",
-           "jtb_final_configs", "jtb_gather_bench", "jtb_host_alloc", "jtb_host_free", "jtb_multi_create", "jtb_multi_create_error", "jtb_multi_destroy", "jtb_multi_n_gpus",
+           "jtb_final_configs", "jtb_gather_bench", "jtb_host_alloc", "jtb_host_free", "jtb_partition_by_key", "jtb_ledger_balances", "jtb_multi_create", "jtb_multi_create_error", "jtb_multi_destroy", "jtb_multi_n_gpus",
            "jtb_multi_last_error", "jtb_multi_check_linearizable", "jtb_multi_check_set_full"]
 
 _lib = None
@@ -194,6 +194,34 @@ class Context:
                  "h2d_bytes", "d2h_bytes", "kernel_launches", "scout_steps", "scout_configs",
                  "scout_decided", "scouts", "engine_level", "beam_levels", "beam_configs", "beam_decided", "beam_attempts"]
         return {n: int(out[i]) for i, n in enumerate(names)}
+
+    # ---- independent/subhistory and ledger->bank on the device ------------------------------
+    def partition_by_key(self, event_key) -> dict:
+        """Stable partition of the events by key: {"order", "shard_off", "key_ids"} (numpy arrays)."""
+        import numpy as np
+        k = np.ascontiguousarray(event_key, dtype=np.int64)
+        n = int(k.shape[0])
+        cap = max(1, n)
+        order = np.empty(n, dtype=np.int32)
+        off = np.empty(cap + 1, dtype=np.int64)
+        ids = np.empty(cap, dtype=np.int64)
+        nk = C.c_int32(0)
+        rc = lib().jtb_partition_by_key(self._h, C.c_int64(n), k.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p),
+                                        off.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p), C.c_int32(cap), C.byref(nk))
+        if rc != 0:
+            raise NativeError(f"jtb_partition_by_key rc={rc}: {self._err()}")
+        return {"order": order, "shard_off": off[:nk.value + 1].copy(), "key_ids": ids[:nk.value].copy()}
+
+    def ledger_balances(self, credits_posted, debits_posted):
+        import numpy as np
+        c = np.ascontiguousarray(credits_posted, dtype=np.int64)
+        d = np.ascontiguousarray(debits_posted, dtype=np.int64)
+        out = np.empty(c.shape[0], dtype=np.int32)
+        rc = lib().jtb_ledger_balances(self._h, C.c_int64(c.shape[0]), c.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                       out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise NativeError(f"jtb_ledger_balances rc={rc}: {self._err()}")
+        return out
 
     # ---- K2 microbenchmark ----------------------------------------------------------------------
     def table_bench(self, n_keys: int, variant: int = 0, rounds: int = 3) -> dict:

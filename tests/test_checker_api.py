@@ -100,3 +100,21 @@ def test_lookup_all_invoked_transfers_and_final_reads():
     assert r["valid?"] is False and len(r["unequal-final-reads"]) == 2
     r = ck.final_reads().check({}, h[:4])                                       # no final reads at all
     assert r["valid?"] is False and r["unequal-final-reads"] == set() and r["unequal-final-lookups"] == set()
+
+
+def test_stats_checker():
+    """(checker/stats), core.clj:144: counts by completion type, overall and by :f; invalid when some :f never succeeded."""
+    from jepsen_tigerbeetle_b200 import checker
+    hist = [
+        {"type": "invoke", "f": "add", "process": 0, "value": 1}, {"type": "ok", "f": "add", "process": 0, "value": 1},
+        {"type": "invoke", "f": "add", "process": 1, "value": 2}, {"type": "info", "f": "add", "process": 1, "value": 2},
+        {"type": "invoke", "f": "read", "process": 0}, {"type": "fail", "f": "read", "process": 0},
+        {"type": "info", "f": "start", "process": "nemesis"},
+    ]
+    r = checker.stats().check({}, hist)
+    assert (r["count"], r["ok-count"], r["fail-count"], r["info-count"]) == (3, 1, 1, 1)
+    assert r["by-f"]["add"] == {"valid?": True, "count": 2, "ok-count": 1, "fail-count": 0, "info-count": 1}
+    assert r["by-f"]["read"]["valid?"] is False and r["valid?"] is False
+    hist.append({"type": "invoke", "f": "read", "process": 0})
+    hist.append({"type": "ok", "f": "read", "process": 0, "value": [1]})
+    assert checker.stats().check({}, hist)["valid?"] is True

@@ -187,7 +187,7 @@ CRASH_HEAVY_VALID = [
     synth.SynthSpec('register', 1000, 24, 902980068, p_info=0.3, tau_think_ns=5e6, n_values=30, stale_read=True),
     synth.SynthSpec('register', 2500, 40, 321354213, p_info=0.1, tau_think_ns=20e6, n_values=30, stale_by=3),
     synth.SynthSpec('cas-register', 1000, 16, 1, p_info=0.05),
-    synth.SynthSpec('cas-register', 50000, 64, 1, p_info=0.3, n_keys=8, grouped_keys=True),      # C5 "monster": 8 keys
+    synth.SynthSpec('cas-register', 50000, 64, 1, p_info=0.3, n_keys=8, grouped_keys=True),      # C5 "monster": 8 keys: no beam
 ]
 
 

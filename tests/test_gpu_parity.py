@@ -456,7 +456,7 @@ def test_scouts_do_not_disturb_exhaustive_counts_or_growth(oracle_mod, monkeypat
     o = oracle_mod.check_linearizable(h, m, 3, eager_reads=True, max_configs=50_000_000)
     assert o["valid"] == H.INVALID
     monkeypatch.setenv("JTB_TABLE_START_MB", "1")
-    with native.Context() as ctx:
+    with native.Context(beam=False) as ctx:      # (the default would settle this one in its budgeted work-list probe)
         g = ctx.check_linearizable(h, m)
         st = ctx.stats()
     same_verdict(g, o)
@@ -521,3 +521,19 @@ def test_linearizable_checker_reports_configs(gpu_ctx):
     assert r["configs"] == [
         {"model": 1, "pending": [{"index": 2}, {"index": 3}], "linearized-open": [], "crashed-linearized": 0},
         {"model": 3, "pending": [{"index": 3}], "linearized-open": [{"index": 2}], "crashed-linearized": 0}]
+
+
+def test_device_partition_by_key_and_ledger_balances(gpu_ctx):
+    """independent/subhistory as ONE stable device partition (vs numpy's stable argsort) and ledger->bank's
+    balance arithmetic (tests/ledger.clj:100-105)."""
+    rng = np.random.default_rng(7)
+    for n, nk in ((0, 1), (1, 1), (1000, 7), (200_000, 64), (300_000, 5000)):
+        keys = rng.choice(np.concatenate([rng.integers(-5, 50, nk), rng.integers(-2**62, 2**62, 3)]), size=n).astype(np.int64) if n else np.zeros(0, np.int64)
+        r = gpu_ctx.partition_by_key(keys)
+        order = np.argsort(keys, kind="stable").astype(np.int32)
+        assert np.array_equal(r["order"], order)
+        ids, first = np.unique(keys[order], return_index=True) if n else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+        assert np.array_equal(r["key_ids"], ids)
+        assert np.array_equal(r["shard_off"], np.concatenate([first, [n]]).astype(np.int64))
+    c = rng.integers(0, 10**9, 100_000); d = rng.integers(0, 10**9, 100_000)
+    assert np.array_equal(gpu_ctx.ledger_balances(c, d), (c - d).astype(np.int32))
