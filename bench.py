@@ -68,7 +68,7 @@ def config_block(args, n_gpus):
                         f"tau_op 10 ms, tau_think {args.think_ms} ms, seed 1+key, "
                         f"{'one stale read (invalid)' if args.invalid else 'linearizable (valid)'}",
             "keys": n_gpus, "sharding": "one key (ledger) per GPU" if n_gpus > 1 else "single key",
-            "l2": "level windows up to 4 GiB and level arrays up to 2 GiB (45 M configurations per level) exceed the 126 MB L2",
+            "l2": "level windows up to 16 GiB and level arrays of 2 GB (45 M configurations per level) exceed the 126 MB L2",
             "model": "bank", "table": "16 B slots, linear probing, per-level window of 16 slots per configuration",
             "engine": "level-synchronous (csrc/jtb_level.cuh)",
             "search_space": "eager-read reduction (product default)" if args.eager_reads else
