@@ -7,6 +7,10 @@
 //   ALGO_WGL     (2)  knossos.wgl: Wing–Gong/Lowe DFS over a doubly linked entry list with
 //                     lift/unlift and a cache of (linearized BitSet, model) — keyed literally on the
 //                     full N-bit set, as Knossos does                                
+//   ALGO_LEVEL   (4)  breadth-first by DEPTH (= number of linearized ops) over literal (linearized BitSet, model)
+//                     configurations, with a visited set that is thrown away after every level: the rule the device's
+//                     level engine relies on ("two equal configurations always have equal depth"), restated on the
+//                     oracle's own data structures — independent of the product's keys, rows and expansion core
 //   ALGO_WGL_COMPACT (3) the same DFS, cache keyed on the exact window form
 //                     (first un-linearized return, mask of open ops, crashed bits, state).  This is
 //                     the TIMED CPU BASELINE (bench.py cpu_baseline / --impl reference): Knossos'
@@ -25,7 +29,7 @@ using namespace jtbo;
 
 namespace {
 
-enum { ALGO_BRUTE = 0, ALGO_LINEAR = 1, ALGO_WGL = 2, ALGO_WGL_COMPACT = 3 };
+enum { ALGO_BRUTE = 0, ALGO_LINEAR = 1, ALGO_WGL = 2, ALGO_WGL_COMPACT = 3, ALGO_LEVEL = 4 };
 
 struct Verdict {
     int valid = JTB_VALID;
@@ -457,6 +461,85 @@ struct WGL {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// ALGO_LEVEL: level-synchronous search, visited set local to a level
+struct LevelBFS {
+    const Shard& sh;
+    bool canon, eager;
+    uint64_t max_configs;
+    LevelBFS(const Shard& s, bool canon_, uint64_t mc, bool eager_) : sh(s), canon(canon_), eager(eager_), max_configs(mc) {}
+
+    struct Cfg {
+        std::vector<uint64_t> lin;
+        State st;
+        SetState ss;
+        std::vector<int> cls_count;
+        int rj = 0;   // first un-linearized return
+    };
+
+    Verdict run() {
+        Verdict v;
+        const int n = (int)sh.ops.size(), n_ret = (int)sh.rets.size();
+        if (n_ret == 0) return v;
+        const bool set_model = sh.model->kind == JTB_MODEL_SET;
+        auto has = [](const Cfg& c, int i) { return (c.lin[i >> 6] >> (i & 63)) & 1ull; };
+        Cfg c0;
+        c0.lin.assign((n + 63) / 64, 0);
+        c0.st = sh.init;
+        c0.ss.cnt.assign(sh.n_elems, 0);
+        c0.cls_count.assign(sh.n_classes, 0);
+        std::vector<Cfg> cur{c0}, nxt;
+        int max_rj = 0;
+        while (!cur.empty()) {
+            std::set<std::string> seen;   // this level only
+            nxt.clear();
+            for (const Cfg& c : cur) {
+                const int frontier_pos = sh.ops[sh.rets[c.rj]].ret_pos;
+                // candidates: un-linearized ops invoked before the first un-linearized return (ops are in invocation order)
+                int only = -1;
+                if (eager) {
+                    for (int i = 0; i < n && sh.ops[i].inv_pos < frontier_pos; ++i) {
+                        const Op& o = sh.ops[i];
+                        if (has(c, i) || o.crashed || o.f != JTB_F_READ) continue;
+                        State st2 = c.st;
+                        SetState ss2 = c.ss;
+                        if (step(sh, o, st2, &ss2)) { only = i; break; }
+                    }
+                }
+                for (int i = 0; i < n && sh.ops[i].inv_pos < frontier_pos; ++i) {
+                    if (only >= 0 && i != only) continue;
+                    const Op& o = sh.ops[i];
+                    if (has(c, i)) continue;
+                    if (canon && o.crashed && c.cls_count[o.cls] != o.rank_in_cls) continue;
+                    Cfg d;
+                    d.st = c.st;
+                    d.ss = c.ss;
+                    if (!step(sh, o, d.st, &d.ss)) continue;
+                    d.lin = c.lin;
+                    d.lin[i >> 6] |= 1ull << (i & 63);
+                    d.cls_count = c.cls_count;
+                    if (o.crashed) d.cls_count[o.cls]++;
+                    d.rj = c.rj;
+                    while (d.rj < n_ret && has(d, sh.rets[d.rj])) ++d.rj;
+                    std::string key(reinterpret_cast<const char*>(d.lin.data()), d.lin.size() * 8);
+                    if (!set_model) key.append(reinterpret_cast<const char*>(&d.st), sizeof(State));
+                    v.probes++;
+                    if (!seen.insert(key).second) continue;
+                    v.configs++;
+                    if (d.rj > max_rj) max_rj = d.rj;
+                    if (d.rj == n_ret) return v;   // every :ok op linearized -> valid
+                    if (max_configs && v.configs >= max_configs) { v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_BUDGET; return v; }
+                    nxt.push_back(std::move(d));
+                }
+            }
+            cur.swap(nxt);
+        }
+        v.valid = JTB_INVALID;
+        v.witness_ret = max_rj;
+        return v;
+    }
+};
+
 void fill(const Shard& sh, const Verdict& v, jtb_lin_shard* out) {
     out->valid = v.valid;
     out->cause = v.cause;
@@ -552,7 +635,7 @@ int jtbo_final_configs(const jtb_history* h, const jtb_model* m, int canon_info,
     }
 }
 
-// algo: 0 brute, 1 linear, 2 wgl (full-bitset cache), 3 wgl compact (timed baseline)
+// algo: 0 brute, 1 linear, 2 wgl (full-bitset cache), 3 wgl compact (timed baseline), 4 level (per-level visited set)
 // canon_info: bit 0 = linearize crashed ops of one class (same f/value) in invocation order only;
 //             bit 1 = eager reads (see WGL::eager; not part of Knossos)
 // n_threads: shards are checked in parallel, one thread per shard at a time (independent/checker)
@@ -575,6 +658,7 @@ int jtbo_check_linearizable(const jtb_history* h, const jtb_model* m, int algo, 
                     case ALGO_LINEAR: v = Linear(sh, max_configs).run(); break;
                     case ALGO_WGL: v = WGL(sh, false, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
                     case ALGO_WGL_COMPACT: v = WGL(sh, true, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
+                    case ALGO_LEVEL: v = LevelBFS(sh, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
                     default: throw std::runtime_error("unknown algo");
                     }
                     fill(sh, v, &shards[s]);

@@ -9,7 +9,7 @@ import pytest
 import kat
 from jepsen_tigerbeetle_b200 import history as H
 
-ALGOS = [0, 1, 2, 3]  # brute, linear, wgl (full bitset), wgl compact
+ALGOS = [0, 1, 2, 3, 4]  # brute, linear, wgl (full bitset), wgl compact, level (per-level visited set)
 
 
 def model_for(name, **kw):
