@@ -8,7 +8,7 @@ import subprocess
 from jepsen_tigerbeetle_b200 import abi
 from jepsen_tigerbeetle_b200.history import CModel, FlatHistory, as_c_history
 
-ALGO_BRUTE, ALGO_LINEAR, ALGO_WGL, ALGO_WGL_COMPACT, ALGO_LEVEL = 0, 1, 2, 3, 4
+ALGO_BRUTE, ALGO_LINEAR, ALGO_WGL, ALGO_WGL_COMPACT, ALGO_LEVEL, ALGO_LAZY_BANK = 0, 1, 2, 3, 4, 5
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 

@@ -11,6 +11,12 @@
 //                     configurations, with a visited set that is thrown away after every level: the rule the device's
 //                     level engine relies on ("two equal configurations always have equal depth"), restated on the
 //                     oracle's own data structures — independent of the product's keys, rows and expansion core
+//   ALGO_LAZY_BANK (5) bank model only (negative balances allowed, no crashed ops, reads of every account): a REDUCED
+//                     search — a transfer is linearized only when the frontier forces it or as part of the exact set
+//                     that makes a read consistent — that visits 10^5 configurations where knossos.wgl visits 10^10.
+//                     Not in Knossos; sound (argument in the struct's comment; verdict and witness equal to knossos.wgl on
+//                     every random history tested).  Its purpose: an independent check of verdict and witness on the
+//                     instances NO exhaustive CPU search can finish (bench headline: tau_think 0)
 //   ALGO_WGL_COMPACT (3) the same DFS, cache keyed on the exact window form
 //                     (first un-linearized return, mask of open ops, crashed bits, state).  This is
 //                     the TIMED CPU BASELINE (bench.py cpu_baseline / --impl reference): Knossos'
@@ -21,6 +27,7 @@
 #include <functional>
 #include <thread>
 #include <atomic>
+#include <array>
 #include <set>
 
 #include "oracle_common.h"
@@ -29,7 +36,7 @@ using namespace jtbo;
 
 namespace {
 
-enum { ALGO_BRUTE = 0, ALGO_LINEAR = 1, ALGO_WGL = 2, ALGO_WGL_COMPACT = 3, ALGO_LEVEL = 4 };
+enum { ALGO_BRUTE = 0, ALGO_LINEAR = 1, ALGO_WGL = 2, ALGO_WGL_COMPACT = 3, ALGO_LEVEL = 4, ALGO_LAZY_BANK = 5 };
 
 struct Verdict {
     int valid = JTB_VALID;
@@ -540,6 +547,142 @@ struct LevelBFS {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// ALGO_LAZY_BANK: "lazy transfers".  With negative balances allowed a transfer never fails and transfers commute, so the
+// state after a set of transfers does not depend on their order, and a read (which reports every balance) pins the
+// state.  Take any linearization and push every transfer as late as it can go: it stops either immediately before a read
+// (together with the other transfers stuck there) or at its real-time deadline, i.e. when it is the frontier op.  So it is
+// enough to search moves of two kinds:  (F) linearize the frontier op if it is a transfer;  (R) for a candidate read r,
+// linearize a set D of pending transfers whose effects sum to exactly expected(r) - balances, then r (D = {}: the
+// eager-read case, taken exclusively).  The furthest frontier reached (the witness) is preserved by the same pushing
+// argument applied to the partial linearization that reaches it.  Configurations are keyed (frontier rank, open-slot mask).
+struct LazyBank {
+    const Shard& sh;
+    uint64_t max_configs;
+    LazyBank(const Shard& s, uint64_t mc) : sh(s), max_configs(mc) {}
+    struct Cfg { int rj; uint64_t mask; int32_t bal[JTB_MAX_ACCOUNTS]; };
+
+    Verdict run() {
+        Verdict v;
+        const jtb_model* m = sh.model;
+        const int n = (int)sh.ops.size(), n_ret = (int)sh.rets.size();
+        if (m->kind != JTB_MODEL_BANK || !m->negative_balances_ok) throw std::runtime_error("lazy-bank: bank model with negative balances allowed only");
+        if (sh.n_slots > 64) { v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_TOO_WIDE; return v; }
+        for (const Op& o : sh.ops) {
+            if (o.crashed) throw std::runtime_error("lazy-bank: histories with crashed ops are not supported");
+            if (o.f == JTB_F_READ && !o.impossible && o.pl_len != 2 * m->n_accounts) throw std::runtime_error("lazy-bank: reads must cover every account");
+        }
+        if (n_ret == 0) return v;
+        std::vector<int> rank(n, -1);
+        for (int j = 0; j < n_ret; ++j) rank[sh.rets[j]] = j;
+        std::vector<std::vector<int>> open_at(n_ret);   // completed ops invoked before the j-th return, returning at or after it
+        {
+            std::vector<int> open;
+            size_t oi = 0;
+            for (int j = 0; j < n_ret; ++j) {
+                const int fpos = sh.ops[sh.rets[j]].ret_pos;
+                while (oi < sh.ops.size() && sh.ops[oi].inv_pos < fpos) open.push_back((int)oi++);
+                open.erase(std::remove_if(open.begin(), open.end(), [&](int i) { return rank[i] < j; }), open.end());
+                open_at[j] = open;
+            }
+        }
+        auto eff = [&](const Op& o, int32_t* d) {
+            const int a = acct_slot(m, o.b), b = acct_slot(m, o.c);
+            if (a >= 0 && b >= 0) { d[a] -= o.a; d[b] += o.a; }
+        };
+        KeySet seen(2);
+        std::vector<Cfg> stack;
+        Cfg c0{};
+        for (int i = 0; i < JTB_MAX_ACCOUNTS; ++i) c0.bal[i] = sh.init.bal[i];
+        stack.push_back(c0);
+        int max_rj = 0;
+        bool found = false;
+        auto push = [&](Cfg c) {
+            while (c.rj < n_ret && ((c.mask >> sh.ops[sh.rets[c.rj]].slot) & 1ull)) { c.mask &= ~(1ull << sh.ops[sh.rets[c.rj]].slot); ++c.rj; }
+            if (c.rj == n_ret) { found = true; return; }
+            const uint64_t key[2] = {(1ull << 63) | (uint64_t)(uint32_t)c.rj, c.mask};
+            v.probes++;
+            if (!seen.insert(key)) return;
+            v.configs++;
+            max_rj = std::max(max_rj, c.rj);
+            stack.push_back(c);
+        };
+        while (!stack.empty() && !found) {
+            if (max_configs && v.configs >= max_configs) { v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_BUDGET; return v; }
+            const Cfg c = stack.back();
+            stack.pop_back();
+            std::vector<int> pend, reads;
+            for (int i : open_at[c.rj]) {
+                if ((c.mask >> sh.ops[i].slot) & 1ull) continue;
+                const Op& o = sh.ops[i];
+                if (o.impossible) continue;
+                if (o.f == JTB_F_TRANSFER) { if (acct_slot(m, o.b) >= 0 && acct_slot(m, o.c) >= 0) pend.push_back(i); }
+                else if (o.f == JTB_F_READ) reads.push_back(i);
+            }
+            bool eager_done = false;   // a read that is consistent as things stand: the only child
+            for (int r : reads) {
+                State st;
+                std::memcpy(st.bal, c.bal, sizeof st.bal);
+                if (step(sh, sh.ops[r], st, nullptr)) { Cfg d = c; d.mask |= 1ull << sh.ops[r].slot; push(d); eager_done = true; break; }
+            }
+            if (eager_done) continue;
+            const int f = sh.rets[c.rj];
+            if (sh.ops[f].f == JTB_F_TRANSFER && !sh.ops[f].impossible && acct_slot(m, sh.ops[f].b) >= 0 && acct_slot(m, sh.ops[f].c) >= 0) {   // (F)
+                Cfg d = c;
+                eff(sh.ops[f], d.bal);
+                d.mask |= 1ull << sh.ops[f].slot;
+                push(d);
+            }
+            const int np = (int)pend.size();   // (R)
+            std::vector<std::array<int32_t, JTB_MAX_ACCOUNTS>> pe(np), up(np + 1), dn(np + 1);
+            for (int k = 0; k < np; ++k) { pe[k].fill(0); eff(sh.ops[pend[k]], pe[k].data()); }
+            up[np].fill(0); dn[np].fill(0);
+            for (int k = np - 1; k >= 0; --k)
+                for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) { up[k][a] = up[k + 1][a] + std::max(pe[k][a], 0); dn[k][a] = dn[k + 1][a] + std::min(pe[k][a], 0); }
+            for (int r : reads) {
+                const Op& ro = sh.ops[r];
+                int32_t delta[JTB_MAX_ACCOUNTS] = {0}, want[JTB_MAX_ACCOUNTS];
+                bool readable = true;
+                std::memcpy(want, c.bal, sizeof want);
+                for (int i = 0; i + 1 < ro.pl_len; i += 2) {
+                    const int sl = acct_slot(m, ro.pl[i]);
+                    if (sl < 0 || ro.pl[i + 1] == JTB_NIL) { readable = false; break; }
+                    want[sl] = ro.pl[i + 1];
+                }
+                if (!readable) continue;
+                for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] = want[a] - c.bal[a];
+                uint64_t dmask = 0;
+                std::function<void(int)> rec = [&](int k) {   // subsets of the pending transfers, bounded by what the rest can still move
+                    bool zero = true;
+                    for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) {
+                        if (delta[a] > up[k][a] || delta[a] < dn[k][a]) return;
+                        zero &= delta[a] == 0;
+                    }
+                    if (zero) {   // D found; a zero-sum superset is reachable from the child (its transfers are still pending there)
+                        Cfg d = c;
+                        d.mask |= dmask | (1ull << ro.slot);
+                        std::memcpy(d.bal, want, sizeof want);
+                        push(d);
+                        return;
+                    }
+                    if (k == np) return;
+                    for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] -= pe[k][a];
+                    dmask |= 1ull << sh.ops[pend[k]].slot;
+                    rec(k + 1);
+                    dmask &= ~(1ull << sh.ops[pend[k]].slot);
+                    for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] += pe[k][a];
+                    rec(k + 1);
+                };
+                rec(0);
+            }
+        }
+        if (found) return v;
+        v.valid = JTB_INVALID;
+        v.witness_ret = max_rj;
+        return v;
+    }
+};
+
 void fill(const Shard& sh, const Verdict& v, jtb_lin_shard* out) {
     out->valid = v.valid;
     out->cause = v.cause;
@@ -658,6 +801,7 @@ int jtbo_check_linearizable(const jtb_history* h, const jtb_model* m, int algo, 
                     case ALGO_LINEAR: v = Linear(sh, max_configs).run(); break;
                     case ALGO_WGL: v = WGL(sh, false, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
                     case ALGO_WGL_COMPACT: v = WGL(sh, true, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
+                    case ALGO_LAZY_BANK: v = LazyBank(sh, max_configs).run(); break;
                     case ALGO_LEVEL: v = LevelBFS(sh, (canon_info & 1) != 0, max_configs, (canon_info & 2) != 0).run(); break;
                     default: throw std::runtime_error("unknown algo");
                     }

@@ -44,7 +44,7 @@ def run_case(name):
     rec = {"case": name, "kind": case["kind"], "events": int(h.n_events), "keys": int(h.n_shards)}
     if case["kind"] == "lin":
         m = BC.model_of(case["model"])
-        r = oracle.check_linearizable(h, m, oracle.ALGO_WGL_COMPACT, max_configs=case.get("max_configs", 0),
+        r = oracle.check_linearizable(h, m, case.get("oracle_algo", oracle.ALGO_WGL_COMPACT), max_configs=case.get("max_configs", 0),
                                       n_threads=case.get("threads", 1), eager_reads=case.get("eager", False))
         rec.update({"valid": r["valid"], "n_failures": r["n_failures"], "configs": r["configs"],
                     "shard_valid": [s["valid"] for s in r["shards"]],
@@ -52,7 +52,8 @@ def run_case(name):
                     "shard_previous_ok": [s["previous_ok_index"] for s in r["shards"]],
                     "shard_configs": [s["configs"] for s in r["shards"]],
                     "shard_cause": [s["cause"] for s in r["shards"]],
-                    "max_configs": case.get("max_configs", 0), "eager": bool(case.get("eager", False))})
+                    "max_configs": case.get("max_configs", 0), "eager": bool(case.get("eager", False)),
+                    "oracle_algo": case.get("oracle_algo", 3), "compare_counts": bool(case.get("compare_counts", True))})
     else:
         r = oracle.check_set_full(h, True)
         rec.update({"valid": r["valid"], "n_failures": r["n_failures"], "shards": r["shards"],
