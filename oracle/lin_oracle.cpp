@@ -11,7 +11,8 @@
 //                     configurations, with a visited set that is thrown away after every level: the rule the device's
 //                     level engine relies on ("two equal configurations always have equal depth"), restated on the
 //                     oracle's own data structures — independent of the product's keys, rows and expansion core
-//   ALGO_LAZY_BANK (5) bank model only (negative balances allowed, no crashed ops, reads of every account): a REDUCED
+//   ALGO_LAZY_BANK (5) bank model only (negative balances allowed, reads of every account; crashed transfers enter only as
+//                     part of a read's set): a REDUCED
 //                     search — a transfer is linearized only when the frontier forces it or as part of the exact set
 //                     that makes a read consistent — that visits 10^5 configurations where knossos.wgl visits 10^10.
 //                     Not in Knossos; sound (argument in the struct's comment; verdict and witness equal to knossos.wgl on
@@ -560,7 +561,9 @@ struct LazyBank {
     const Shard& sh;
     uint64_t max_configs;
     LazyBank(const Shard& s, uint64_t mc) : sh(s), max_configs(mc) {}
-    struct Cfg { int rj; uint64_t mask; int32_t bal[JTB_MAX_ACCOUNTS]; };
+    // crashed (:info) transfers are never forced; they only ever enter as part of a read's set D, members of one class
+    // (same debit, credit, amount) in invocation order — so a configuration also records how many of each class it consumed
+    struct Cfg { int rj; uint64_t mask; int32_t bal[JTB_MAX_ACCOUNTS]; std::vector<uint16_t> used; };
 
     Verdict run() {
         Verdict v;
@@ -568,10 +571,8 @@ struct LazyBank {
         const int n = (int)sh.ops.size(), n_ret = (int)sh.rets.size();
         if (m->kind != JTB_MODEL_BANK || !m->negative_balances_ok) throw std::runtime_error("lazy-bank: bank model with negative balances allowed only");
         if (sh.n_slots > 64) { v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_TOO_WIDE; return v; }
-        for (const Op& o : sh.ops) {
-            if (o.crashed) throw std::runtime_error("lazy-bank: histories with crashed ops are not supported");
-            if (o.f == JTB_F_READ && !o.impossible && o.pl_len != 2 * m->n_accounts) throw std::runtime_error("lazy-bank: reads must cover every account");
-        }
+        for (const Op& o : sh.ops)
+            if (!o.crashed && o.f == JTB_F_READ && !o.impossible && o.pl_len != 2 * m->n_accounts) throw std::runtime_error("lazy-bank: reads must cover every account");
         if (n_ret == 0) return v;
         std::vector<int> rank(n, -1);
         for (int j = 0; j < n_ret; ++j) rank[sh.rets[j]] = j;
@@ -581,42 +582,47 @@ struct LazyBank {
             size_t oi = 0;
             for (int j = 0; j < n_ret; ++j) {
                 const int fpos = sh.ops[sh.rets[j]].ret_pos;
-                while (oi < sh.ops.size() && sh.ops[oi].inv_pos < fpos) open.push_back((int)oi++);
+                while (oi < sh.ops.size() && sh.ops[oi].inv_pos < fpos) { if (!sh.ops[oi].crashed) open.push_back((int)oi); ++oi; }
                 open.erase(std::remove_if(open.begin(), open.end(), [&](int i) { return rank[i] < j; }), open.end());
                 open_at[j] = open;
             }
         }
-        auto eff = [&](const Op& o, int32_t* d) {
-            const int a = acct_slot(m, o.b), b = acct_slot(m, o.c);
-            if (a >= 0 && b >= 0) { d[a] -= o.a; d[b] += o.a; }
-        };
-        KeySet seen(2);
+        auto usable = [&](const Op& o) { return o.f == JTB_F_TRANSFER && !o.impossible && acct_slot(m, o.b) >= 0 && acct_slot(m, o.c) >= 0; };
+        auto eff = [&](const Op& o, int32_t* d) { d[acct_slot(m, o.b)] -= o.a; d[acct_slot(m, o.c)] += o.a; };
+        const int ncls = sh.n_classes;
+        std::set<std::string> seen;
         std::vector<Cfg> stack;
         Cfg c0{};
         for (int i = 0; i < JTB_MAX_ACCOUNTS; ++i) c0.bal[i] = sh.init.bal[i];
+        c0.used.assign(ncls, 0);
         stack.push_back(c0);
         int max_rj = 0;
         bool found = false;
         auto push = [&](Cfg c) {
             while (c.rj < n_ret && ((c.mask >> sh.ops[sh.rets[c.rj]].slot) & 1ull)) { c.mask &= ~(1ull << sh.ops[sh.rets[c.rj]].slot); ++c.rj; }
             if (c.rj == n_ret) { found = true; return; }
-            const uint64_t key[2] = {(1ull << 63) | (uint64_t)(uint32_t)c.rj, c.mask};
+            std::string key(reinterpret_cast<const char*>(&c.rj), 4);
+            key.append(reinterpret_cast<const char*>(&c.mask), 8);
+            key.append(reinterpret_cast<const char*>(c.used.data()), c.used.size() * 2);
             v.probes++;
-            if (!seen.insert(key)) return;
+            if (!seen.insert(key).second) return;
             v.configs++;
             max_rj = std::max(max_rj, c.rj);
-            stack.push_back(c);
+            stack.push_back(std::move(c));
         };
+        struct Item { int op; int cls; };   // cls >= 0: the next unused members of a crashed class, in invocation order
         while (!stack.empty() && !found) {
             if (max_configs && v.configs >= max_configs) { v.valid = JTB_UNKNOWN; v.cause = JTB_CAUSE_BUDGET; return v; }
             const Cfg c = stack.back();
             stack.pop_back();
-            std::vector<int> pend, reads;
+            const int fpos = sh.ops[sh.rets[c.rj]].ret_pos;
+            std::vector<Item> pend;
+            std::vector<int> reads;
             for (int i : open_at[c.rj]) {
                 if ((c.mask >> sh.ops[i].slot) & 1ull) continue;
                 const Op& o = sh.ops[i];
                 if (o.impossible) continue;
-                if (o.f == JTB_F_TRANSFER) { if (acct_slot(m, o.b) >= 0 && acct_slot(m, o.c) >= 0) pend.push_back(i); }
+                if (o.f == JTB_F_TRANSFER) { if (usable(o)) pend.push_back(Item{i, -1}); }
                 else if (o.f == JTB_F_READ) reads.push_back(i);
             }
             bool eager_done = false;   // a read that is consistent as things stand: the only child
@@ -627,15 +633,23 @@ struct LazyBank {
             }
             if (eager_done) continue;
             const int f = sh.rets[c.rj];
-            if (sh.ops[f].f == JTB_F_TRANSFER && !sh.ops[f].impossible && acct_slot(m, sh.ops[f].b) >= 0 && acct_slot(m, sh.ops[f].c) >= 0) {   // (F)
+            if (usable(sh.ops[f])) {   // (F)
                 Cfg d = c;
                 eff(sh.ops[f], d.bal);
                 d.mask |= 1ull << sh.ops[f].slot;
                 push(d);
             }
+            for (int cl = 0; cl < ncls; ++cl) {   // crashed transfers invoked so far and not consumed yet, class by class
+                const std::vector<int>& mem = sh.cls_members[cl];
+                for (int k = c.used[cl]; k < (int)mem.size(); ++k) {
+                    const Op& o = sh.ops[mem[k]];
+                    if (o.inv_pos >= fpos || !usable(o)) break;
+                    pend.push_back(Item{mem[k], cl});
+                }
+            }
             const int np = (int)pend.size();   // (R)
             std::vector<std::array<int32_t, JTB_MAX_ACCOUNTS>> pe(np), up(np + 1), dn(np + 1);
-            for (int k = 0; k < np; ++k) { pe[k].fill(0); eff(sh.ops[pend[k]], pe[k].data()); }
+            for (int k = 0; k < np; ++k) { pe[k].fill(0); eff(sh.ops[pend[k].op], pe[k].data()); }
             up[np].fill(0); dn[np].fill(0);
             for (int k = np - 1; k >= 0; --k)
                 for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) { up[k][a] = up[k + 1][a] + std::max(pe[k][a], 0); dn[k][a] = dn[k + 1][a] + std::min(pe[k][a], 0); }
@@ -652,6 +666,7 @@ struct LazyBank {
                 if (!readable) continue;
                 for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] = want[a] - c.bal[a];
                 uint64_t dmask = 0;
+                std::vector<uint16_t> used = c.used;
                 std::function<void(int)> rec = [&](int k) {   // subsets of the pending transfers, bounded by what the rest can still move
                     bool zero = true;
                     for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) {
@@ -661,17 +676,25 @@ struct LazyBank {
                     if (zero) {   // D found; a zero-sum superset is reachable from the child (its transfers are still pending there)
                         Cfg d = c;
                         d.mask |= dmask | (1ull << ro.slot);
+                        d.used = used;
                         std::memcpy(d.bal, want, sizeof want);
                         push(d);
                         return;
                     }
                     if (k == np) return;
-                    for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] -= pe[k][a];
-                    dmask |= 1ull << sh.ops[pend[k]].slot;
-                    rec(k + 1);
-                    dmask &= ~(1ull << sh.ops[pend[k]].slot);
-                    for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] += pe[k][a];
-                    rec(k + 1);
+                    const Item it = pend[k];
+                    // take it (a crashed member only when every earlier member of its class is taken: its turn)
+                    if (it.cls < 0 || sh.ops[it.op].rank_in_cls == used[it.cls]) {
+                        for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] -= pe[k][a];
+                        if (it.cls < 0) dmask |= 1ull << sh.ops[it.op].slot; else used[it.cls]++;
+                        rec(k + 1);
+                        if (it.cls < 0) dmask &= ~(1ull << sh.ops[it.op].slot); else used[it.cls]--;
+                        for (int a = 0; a < JTB_MAX_ACCOUNTS; ++a) delta[a] += pe[k][a];
+                    }
+                    // skip it (and with it the later members of its class: they are interchangeable)
+                    int k2 = k + 1;
+                    if (it.cls >= 0) while (k2 < np && pend[k2].cls == it.cls) ++k2;
+                    rec(k2);
                 };
                 rec(0);
             }
