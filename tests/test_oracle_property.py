@@ -156,3 +156,22 @@ def test_lazy_bank_decider_equals_knossos_wgl(oracle_mod):
     h = synth.generate(synth.SynthSpec("bank", 10000, 32, 1, tau_think_ns=0, stale_read=True))
     r = oracle_mod.check_linearizable(h, m, 5)
     assert r["valid"] == H.INVALID and r["shards"][0]["witness_index"] == 18016 and r["configs"] < 1_000_000
+
+
+def test_lazy_bank_decider_with_crashed_transfers(oracle_mod):
+    """Crashed (:info) transfers enter the reduced search only as part of a read's set, class members in invocation
+    order: verdict, witness and previous-ok must still equal knossos.wgl's."""
+    m = H.make_model(H.MODEL_BANK, accounts=range(1, 9))
+    n_invalid = 0
+    for seed in range(160):
+        spec = synth.SynthSpec("bank", n_ops=30 + seed % 70, n_clients=2 + seed % 8, seed=1000 + seed, stale_read=seed % 2 == 0,
+                               stale_by=2 + seed % 6, tau_think_ns=(seed % 5) * 2e6, p_info=(0.05, 0.15, 0.3)[seed % 3])
+        h = synth.generate(spec)
+        a = oracle_mod.check_linearizable(h, m, 3, max_configs=3_000_000)
+        if a["valid"] == H.UNKNOWN:
+            continue
+        b = oracle_mod.check_linearizable(h, m, 5, max_configs=3_000_000)
+        assert (a["valid"], a["shards"][0]["witness_index"], a["shards"][0]["previous_ok_index"]) == \
+               (b["valid"], b["shards"][0]["witness_index"], b["shards"][0]["previous_ok_index"]), seed
+        n_invalid += a["valid"] == H.INVALID
+    assert n_invalid > 20
