@@ -117,8 +117,12 @@
 ;; one context per device is enough (jtb_ctx holds a mutex).  `*n-gpus*` > 1 selects the in-library fan-out
 ;; (jtb_multi_*: shards partitioned over the GPUs, one NCCL all-reduce(MAX) of the verdict vector).
 (def ^:dynamic *n-gpus* 1)
-(defonce ^:private ctx   (delay (Native/create 0 0 0 0 0)))
-(defonce ^:private multi (delay (Native/multiCreate 0 0 0 0 0)))
+;; jtb_opts.flags (include/jtb_check.h, Native/OPT_*): 0 = defaults — eager reads, engine chosen from the history (level
+;; engine for exhaustive sweeps, work list + beam + scouts for histories with crashed ops).  Rebind before first use, e.g.
+;; (bit-or Native/OPT_NO_EAGER_READS Native/OPT_ENGINE_LEVEL) to sweep exactly the configurations Knossos would visit.
+(def ^:dynamic *flags* 0)
+(defonce ^:private ctx   (delay (Native/create 0 (int *flags*) 0 0 0)))
+(defonce ^:private multi (delay (Native/multiCreate 0 (int *flags*) 0 0 0)))
 (defn- handle [] (if (> *n-gpus* 1) [@multi true] [@ctx false]))
 
 (defn- model-args [model test]
